@@ -1,0 +1,136 @@
+"""Mirror of the reference's `fields` package.
+ref: src/fields/surface_field.py:27-116, src/fields/radiance_field.py:25-81, src/fields/nerf_field.py:35-105
+"""
+from dataclasses import dataclass, field
+from typing import Optional, Type
+
+import torch
+
+from .configs import InstantiateConfig
+from .field_components import (EncodingConfig, FieldComponent, FieldComponentConfig, MLPConfig, ModalityHeadConfig,
+                               NeRFEncodingConfig)
+
+
+@dataclass
+class SurfaceFieldConfig(InstantiateConfig):
+    _target: Type = field(default_factory=lambda: SurfaceField)
+    use_position_encoding: bool = True
+    position_encoding: EncodingConfig = field(default_factory=lambda: NeRFEncodingConfig)
+    geo_feature_dim: int = 256
+    field: FieldComponentConfig = field(default_factory=lambda: MLPConfig)
+
+
+@dataclass
+class SDFFieldConfig(SurfaceFieldConfig):
+    _target: Type = field(default_factory=lambda: SDFField)
+    inside_outside: bool = False
+
+
+class SurfaceField(torch.nn.Module):
+    def __init__(self, config: SurfaceFieldConfig):
+        super().__init__()
+        self.config = config
+        self.position_encoding = self.config.position_encoding.setup(in_dim=3)
+        self.input_dim = self.position_encoding.get_out_dim() if self.config.use_position_encoding else 3
+        self.output_dim = 1 + self.config.geo_feature_dim if self.config.geo_feature_dim is not None else 1
+
+    def single_output(self, x):
+        return self.forward(x, sdf_only=True)[0]
+
+    def get_training_callbacks(self, training_callback_attributes):
+        return self.field.get_training_callbacks(training_callback_attributes)
+
+    def get_model_parameters(self):
+        return self.field.get_model_parameters()
+
+
+class SDFField(SurfaceField):
+    """ref: surface_field.py:86-116.  `sdf_only=True` evaluates just the first output of the last
+    layer (what `single_output` keeps) instead of computing and discarding the 256 geometry features."""
+
+    def __init__(self, config: SDFFieldConfig):
+        super().__init__(config)
+        self.field = self.config.field.setup(input_dim=self.input_dim, output_dim=self.output_dim)
+
+    def forward(self, x, sdf_only: bool = False):
+        if self.config.use_position_encoding:
+            x = self.position_encoding(x)
+        if sdf_only:
+            return self.field(x, n_out_used=1), None
+        out = self.field(x)
+        if self.config.geo_feature_dim is not None:
+            sdf, geo_feature = torch.split(out, [1, self.config.geo_feature_dim], dim=-1)
+        else:
+            sdf, geo_feature = out, None
+        return sdf, geo_feature
+
+
+@dataclass
+class BaseRadianceFieldConfig(FieldComponentConfig):
+    _target: Type = field(default_factory=lambda: RadianceField)
+
+
+@dataclass
+class RadianceFieldConfig(BaseRadianceFieldConfig):
+    _target: Type = field(default_factory=lambda: RadianceField)
+    base_field: FieldComponentConfig = field(default_factory=lambda: MLPConfig)
+
+
+class RadianceField(FieldComponent):
+    """ref: radiance_field.py:55-81"""
+
+    def __init__(self, config: RadianceFieldConfig, position_dim=3, view_direction_dim=3, additional_input_dim=0,
+                 output_dim: int = 3):
+        input_dim = position_dim + view_direction_dim + additional_input_dim
+        super().__init__(config, input_dim=input_dim, output_dim=output_dim)
+        self.base_field = self.config.base_field.setup(input_dim=self.input_dim, output_dim=self.output_dim)
+
+    def forward(self, positions, view_directions, additional_inputs):
+        inputs = torch.cat([positions, view_directions, additional_inputs], dim=-1)
+        return self.base_field(inputs)
+
+    def get_training_callbacks(self, training_callback_attributes):
+        return self.base_field.get_training_callbacks(training_callback_attributes)
+
+    def get_model_parameters(self):
+        return self.base_field.get_model_parameters()
+
+
+@dataclass
+class NeRFFieldConfig(FieldComponentConfig):
+    _target: Type = field(default_factory=lambda: NeRFField)
+    base_field: FieldComponentConfig = field(default_factory=lambda: MLPConfig)
+    head_field: FieldComponentConfig = field(default_factory=lambda: MLPConfig)
+    use_position_encoding: bool = True
+    position_encoding: EncodingConfig = field(default_factory=lambda: NeRFEncodingConfig)
+    use_direction_encoding: bool = True
+    direction_encoding: EncodingConfig = field(default_factory=lambda: NeRFEncodingConfig)
+
+
+class NeRFField(torch.nn.Module):
+    """ref: nerf_field.py:53-105"""
+
+    def __init__(self, config: NeRFFieldConfig, radiance_output_dim: int = 3):
+        super().__init__()
+        self.config = config
+        self.position_encoding = self.config.position_encoding.setup(in_dim=3)
+        self.direction_encoding = self.config.direction_encoding.setup(in_dim=3)
+        base_input = self.position_encoding.get_out_dim() if self.config.use_position_encoding else 3
+        head_input = self.config.base_field.output_dim + self.direction_encoding.get_out_dim() \
+            if self.config.use_direction_encoding else 3 + self.config.base_field.output_dim
+        self.base_field = self.config.base_field.setup(input_dim=base_input, output_dim=self.config.base_field.output_dim)
+        self.head_field = self.config.head_field.setup(input_dim=head_input, output_dim=radiance_output_dim)
+        self.density_head = ModalityHeadConfig(
+            field=MLPConfig(num_layers=1, hidden_dim=64, weight_norm=True, out_activation="Softplus")
+        ).setup(input_dim=self.base_field.output_dim, output_dim=1)
+
+    def forward(self, x, viewing_direction):
+        if self.config.use_position_encoding:
+            x = self.position_encoding(x)
+        if self.config.use_direction_encoding:
+            viewing_direction = self.direction_encoding(viewing_direction)
+        feature = self.base_field(x)
+        density = self.density_head(feature)
+        head_input = torch.cat([feature, viewing_direction], dim=-1)
+        feature = self.head_field(head_input)
+        return density, feature

@@ -1,0 +1,668 @@
+"""Autograd wrappers over the C ABI (include/mms_b200.h): one `torch.autograd.Function` per operator
+of the hot path.  PyTorch only supplies device memory, the current stream and the autograd tape;
+all arithmetic runs in libmms_b200.so.  Non-CUDA tensors raise (no fallback).
+"""
+import ctypes
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MmsbHashGridDesc, call, ptr, stream_ptr
+
+ACT = {"None": 0, None: 0, "ReLU": 1, "Softplus": 2, "Sigmoid": 3}
+INTERP = {"Linear": 0, None: 0, "Smoothstep": 1}
+SPACING_UNIFORM, SPACING_DISPARITY = 0, 1
+
+_i32, _i64, _f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+
+
+def _f(t: torch.Tensor) -> torch.Tensor:
+    """fp32 contiguous CUDA view/copy of t."""
+    if not t.is_cuda:
+        raise ValueError("mms_b200 ops need CUDA tensors (no CPU fallback)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _rows(t: torch.Tensor, last: int) -> torch.Tensor:
+    """[..., last] -> contiguous [n, last]"""
+    if t.shape[-1] != last:
+        raise ValueError(f"expected last dimension {last}, got {tuple(t.shape)}")
+    return _f(t).reshape(-1, last)
+
+
+# ------------------------------------------------------------------------------------------------
+# hash grid (A9/A10)
+# ------------------------------------------------------------------------------------------------
+def hash_resolutions(min_res: int, max_res: int, num_levels: int) -> List[float]:
+    """floor(min_res * growth**l) exactly as the reference evaluates it (encodings.py:195-197,227):
+    growth in float64 numpy, the power/product/floor on a float32 torch tensor."""
+    growth = np.exp((np.log(max_res) - np.log(min_res)) / (num_levels - 1)) if num_levels > 1 else 1.0
+    levels = torch.arange(num_levels)
+    return torch.floor(min_res * growth ** levels).to(torch.float32).tolist()
+
+
+def make_hashgrid_desc(num_levels, features_per_level, log2_hashmap_size, resolutions, radius=0.0,
+                       interpolation="Linear") -> MmsbHashGridDesc:
+    if interpolation not in INTERP:
+        raise ValueError(f"interpolation '{interpolation}' is not supported")
+    d = MmsbHashGridDesc()
+    d.num_levels = int(num_levels)
+    d.features_per_level = int(features_per_level)
+    d.log2_hashmap_size = int(log2_hashmap_size)
+    d.interpolation = INTERP[interpolation]
+    d.radius = float(radius)
+    for i, r in enumerate(resolutions):
+        d.resolution[i] = float(r)
+    return d
+
+
+def hashgrid_fwd_into(desc, x, table, mask, out, col_offset=0, idx_out=None):
+    """Writes the L*F features of x [n,3] into out[:, col_offset:col_offset+L*F] (row stride = out.stride(0))."""
+    n = x.shape[0]
+    out_view = out[:, col_offset:]
+    call("mmsb_hashgrid_fwd", ctypes.byref(desc), ptr(x), _i64(x.stride(0)), ptr(table), ptr(mask),
+         ptr(out_view), _i64(out.stride(0)), ptr(idx_out), _i64(n), stream_ptr())
+
+
+def hashgrid_bwd_from(desc, x, table, mask, dout, col_offset, dtable, dx):
+    n = x.shape[0]
+    dview = dout[:, col_offset:]
+    call("mmsb_hashgrid_bwd", ctypes.byref(desc), ptr(x), _i64(x.stride(0)), ptr(table), ptr(mask),
+         ptr(dview), _i64(dout.stride(0)), ptr(dtable), ptr(dx), _i64(dx.stride(0) if dx is not None else 3),
+         _i64(n), stream_ptr())
+
+
+class HashGridFn(torch.autograd.Function):
+    """features = HashEncoding(x) [* level mask, after the FeatureGrid rescale when desc.radius > 0]."""
+
+    @staticmethod
+    def forward(ctx, x, table, mask, desc):
+        x2 = _rows(x, 3)
+        table = _f(table)
+        nf = desc.num_levels * desc.features_per_level
+        out = torch.empty((x2.shape[0], nf), device=x2.device, dtype=torch.float32)
+        hashgrid_fwd_into(desc, x2, table, mask, out)
+        ctx.save_for_backward(x2, table, mask)
+        ctx.desc = desc
+        ctx.x_shape = x.shape
+        return out.reshape(*x.shape[:-1], nf)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, table, mask = ctx.saved_tensors
+        desc = ctx.desc
+        nf = desc.num_levels * desc.features_per_level
+        dout = _f(dout).reshape(-1, nf)
+        dtable = torch.zeros_like(table) if ctx.needs_input_grad[1] else None
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        if dtable is not None or dx is not None:
+            hashgrid_bwd_from(desc, x2, table, mask, dout, 0, dtable, dx)
+        return (dx.reshape(ctx.x_shape) if dx is not None else None), dtable, None, None
+
+
+def hashgrid_indices(desc, x, table):
+    """int64 [n, L, 8] corner rows (reference order hashed_0..7) — parity surface."""
+    x2 = _rows(x, 3)
+    nf = desc.num_levels * desc.features_per_level
+    out = torch.empty((x2.shape[0], nf), device=x2.device, dtype=torch.float32)
+    idx = torch.empty((x2.shape[0], desc.num_levels, 8), device=x2.device, dtype=torch.int64)
+    hashgrid_fwd_into(desc, x2, _f(table), None, out, 0, idx)
+    return idx, out
+
+
+# ------------------------------------------------------------------------------------------------
+# NeRF / SH encodings (A8, A15)
+# ------------------------------------------------------------------------------------------------
+def nerf_freqs(min_freq_exp, max_freq_exp, num_frequencies):
+    return (2 ** torch.linspace(min_freq_exp, max_freq_exp, num_frequencies)).to(torch.float32).tolist()
+
+
+def nerf_out_dim(in_dim, num_freqs, include_input):
+    return in_dim * num_freqs * 2 + (in_dim if include_input else 0)
+
+
+def nerf_fwd_into(x, freqs, include_input, out, col_offset=0):
+    n, d = x.shape
+    fr = (_f32 * len(freqs))(*freqs)
+    call("mmsb_nerf_encoding_fwd", ptr(x), _i64(x.stride(0)), _i32(d), fr, _i32(len(freqs)), _i32(int(include_input)),
+         ptr(out[:, col_offset:]), _i64(out.stride(0)), _i64(n), stream_ptr())
+
+
+def nerf_bwd_from(x, freqs, include_input, dout, col_offset, dx, accumulate):
+    n, d = x.shape
+    fr = (_f32 * len(freqs))(*freqs)
+    call("mmsb_nerf_encoding_bwd", ptr(x), _i64(x.stride(0)), _i32(d), fr, _i32(len(freqs)), _i32(int(include_input)),
+         ptr(dout[:, col_offset:]), _i64(dout.stride(0)), ptr(dx), _i64(dx.stride(0)), _i32(int(accumulate)), _i64(n),
+         stream_ptr())
+
+
+class NerfEncodingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, freqs, include_input):
+        d = x.shape[-1]
+        x2 = _rows(x, d)
+        od = nerf_out_dim(d, len(freqs), include_input)
+        out = torch.empty((x2.shape[0], od), device=x2.device, dtype=torch.float32)
+        nerf_fwd_into(x2, freqs, include_input, out)
+        ctx.save_for_backward(x2)
+        ctx.cfg = (tuple(freqs), include_input, x.shape, od)
+        return out.reshape(*x.shape[:-1], od)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x2,) = ctx.saved_tensors
+        freqs, include_input, shape, od = ctx.cfg
+        dx = torch.empty_like(x2)
+        nerf_bwd_from(x2, list(freqs), include_input, _f(dout).reshape(-1, od), 0, dx, False)
+        return dx.reshape(shape), None, None
+
+
+class SHEncodingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dirs, levels):
+        d2 = _rows(dirs, 3)
+        nc = levels * levels
+        out = torch.empty((d2.shape[0], nc), device=d2.device, dtype=torch.float32)
+        call("mmsb_sh_encoding_fwd", ptr(d2), _i64(3), _i32(levels), ptr(out), _i64(nc), _i64(d2.shape[0]), stream_ptr())
+        ctx.save_for_backward(d2)
+        ctx.cfg = (levels, dirs.shape)
+        return out.reshape(*dirs.shape[:-1], nc)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (d2,) = ctx.saved_tensors
+        levels, shape = ctx.cfg
+        nc = levels * levels
+        dd = torch.empty_like(d2)
+        g = _f(dout).reshape(-1, nc)
+        call("mmsb_sh_encoding_bwd", ptr(d2), _i64(3), _i32(levels), ptr(g), _i64(nc), ptr(dd), _i64(3),
+             _i64(d2.shape[0]), stream_ptr())
+        return dd.reshape(shape), None
+
+
+# ------------------------------------------------------------------------------------------------
+# MLP (A11)
+# ------------------------------------------------------------------------------------------------
+def linear_fwd(x, w, b, act, act_param, out=None):
+    n, k = x.shape
+    o = w.shape[0]
+    if out is None:
+        out = torch.empty((n, o), device=x.device, dtype=torch.float32)
+    call("mmsb_linear_fwd", ptr(x), _i64(x.stride(0)), ptr(w), ptr(b), ptr(out), _i64(out.stride(0)), _i64(n), _i32(k),
+         _i32(o), _i32(act), _f32(act_param), stream_ptr())
+    return out
+
+
+class MLPFn(torch.autograd.Function):
+    """y = MLP(x): layers [(W_i [out,in], b_i)], hidden activation, output activation, optional
+    skip connections (the layer input becomes cat([h, x]) / sqrt(2), mlp.py:164-165).
+    args = (x, hidden_act, act_param, out_act, skips(tuple), n_out_used, W0, b0, W1, b1, ...)
+    n_out_used: if not None only the first n_out_used outputs of the last layer are evaluated
+    (the sdf-only evaluations of surface_model.py:143-146 / get_sdf)."""
+
+    @staticmethod
+    def forward(ctx, x, hidden_act, act_param, out_act, skips, n_out_used, *params):
+        nl = len(params) // 2
+        in_dim = x.shape[-1]
+        x2 = _rows(x, in_dim)
+        ws = [_f(params[2 * i]) for i in range(nl)]
+        bs = [_f(params[2 * i + 1]) if params[2 * i + 1] is not None else None for i in range(nl)]
+        if n_out_used is not None:
+            ws[-1] = ws[-1][:n_out_used].contiguous()
+            bs[-1] = bs[-1][:n_out_used].contiguous() if bs[-1] is not None else None
+        acts_in = [x2]       # input of every layer
+        h = x2
+        for i in range(nl):
+            if i in skips:
+                h = torch.cat([h, x2], -1) / math.sqrt(2)
+                acts_in[i] = h
+            a = hidden_act if i < nl - 1 else out_act
+            h = linear_fwd(h, ws[i], bs[i], a, act_param)
+            acts_in.append(h)
+        ctx.save_for_backward(*acts_in, *ws)
+        ctx.cfg = (nl, hidden_act, act_param, out_act, tuple(skips), n_out_used, x.shape, in_dim,
+                   [p is not None for p in params], [tuple(params[2 * i].shape) for i in range(nl)])
+        return h.reshape(*x.shape[:-1], h.shape[-1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        nl, hidden_act, act_param, out_act, skips, n_out_used, x_shape, in_dim, has, wshapes = ctx.cfg
+        saved = ctx.saved_tensors
+        acts = saved[: nl + 1]
+        ws = saved[nl + 1:]
+        x2 = acts[0] if 0 not in skips else None
+        n = acts[0].shape[0]
+        out_dim = acts[nl].shape[1]
+        dz = _f(dy).reshape(n, out_dim)
+        # activation derivative of the output layer
+        if out_act != 0:
+            dz_new = torch.empty_like(dz)
+            call("mmsb_act_bwd", ptr(dz), _i64(out_dim), ptr(acts[nl]), _i64(out_dim), ptr(dz_new), _i64(out_dim),
+                 _i64(n), _i32(out_dim), _i32(out_act), _f32(act_param), stream_ptr())
+            dz = dz_new
+        grads = [None] * (2 * nl)
+        dx_skip = None
+        need_dx = ctx.needs_input_grad[0]
+        for i in range(nl - 1, -1, -1):
+            w = ws[i]
+            o, k = w.shape
+            xin = acts[i]
+            if ctx.needs_input_grad[6 + 2 * i] or (has[2 * i + 1] and ctx.needs_input_grad[7 + 2 * i]):
+                dw = torch.zeros((o, k), device=w.device, dtype=torch.float32)
+                db = torch.zeros((o,), device=w.device, dtype=torch.float32) if has[2 * i + 1] else None
+                call("mmsb_linear_bwd_weight", ptr(dz), _i64(dz.stride(0)), ptr(xin), _i64(xin.stride(0)), ptr(dw),
+                     ptr(db), _i64(n), _i32(k), _i32(o), stream_ptr())
+                if i == nl - 1 and n_out_used is not None:
+                    full_w = torch.zeros(wshapes[i], device=w.device, dtype=torch.float32)
+                    full_w[:n_out_used] = dw
+                    dw = full_w
+                    if db is not None:
+                        full_b = torch.zeros((wshapes[i][0],), device=w.device, dtype=torch.float32)
+                        full_b[:n_out_used] = db
+                        db = full_b
+                grads[2 * i] = dw
+                grads[2 * i + 1] = db
+            if i == 0 and not need_dx:
+                break
+            dxin = torch.empty((n, k), device=w.device, dtype=torch.float32)
+            # the input of layer i is the hidden activation of layer i-1 (unless a skip concat sits between)
+            fuse_prev = i > 0 and i not in skips
+            call("mmsb_linear_bwd_data", ptr(dz), _i64(dz.stride(0)), ptr(w), ptr(dxin), _i64(k),
+                 ptr(xin) if fuse_prev else None, _i64(xin.stride(0)), _i32(hidden_act if fuse_prev else 0),
+                 _f32(act_param), _i64(n), _i32(k), _i32(o), stream_ptr())
+            if i in skips:
+                dxin = dxin / math.sqrt(2)
+                hk = k - in_dim
+                d_skip = dxin[:, hk:]
+                dx_skip = d_skip if dx_skip is None else dx_skip + d_skip
+                dh = dxin[:, :hk].contiguous()
+                if i > 0:
+                    hprev = acts[i][:, :hk] * math.sqrt(2)   # undo the /sqrt(2) to recover y_{i-1}
+                    dz = torch.empty_like(dh)
+                    call("mmsb_act_bwd", ptr(dh), _i64(hk), ptr(hprev.contiguous()), _i64(hk), ptr(dz), _i64(hk), _i64(n),
+                         _i32(hk), _i32(hidden_act), _f32(act_param), stream_ptr())
+                else:
+                    dz = dh
+            else:
+                dz = dxin
+        dx = None
+        if need_dx:
+            dx = dz if dx_skip is None else dz + dx_skip
+            dx = dx.reshape(x_shape)
+        return (dx, None, None, None, None, None, *grads)
+
+
+def mlp_forward(x, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]], hidden_act: str,
+                out_act: Optional[str], act_param: float = 1.0, skips=(), n_out_used=None):
+    params = []
+    for w, b in zip(weights, biases):
+        params += [w, b]
+    return MLPFn.apply(x, ACT[hidden_act], float(act_param), ACT[out_act], tuple(skips), n_out_used, *params)
+
+
+# ------------------------------------------------------------------------------------------------
+# ray generation / collider (A1-A3)
+# ------------------------------------------------------------------------------------------------
+class RayGenFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coords, c2w, intr, dist, pose_adjust, pixel_offset):
+        n = coords.shape[0]
+        dev = coords.device
+        coords = coords.to(torch.int32).contiguous()
+        c2w, intr = _f(c2w), _f(intr)
+        dist = _f(dist) if dist is not None else None
+        pa = _f(pose_adjust) if pose_adjust is not None else None
+        n_cam = c2w.shape[0]
+        n_pose = pa.shape[0] if pa is not None else 0
+        o = torch.empty((n, 3), device=dev)
+        d = torch.empty((n, 3), device=dev)
+        up = torch.empty((n, 3), device=dev)
+        area = torch.empty((n, 1), device=dev)
+        dn = torch.empty((n, 1), device=dev)
+        call("mmsb_raygen_fwd", ptr(coords), ptr(c2w), ptr(intr), ptr(dist), ptr(pa), _i32(n_pose), _i32(n_cam),
+             _f32(pixel_offset), ptr(o), ptr(d), ptr(up), ptr(area), ptr(dn), _i64(n), stream_ptr())
+        ctx.save_for_backward(coords, c2w, intr, dist, pa)
+        ctx.cfg = (n_pose, n_cam, float(pixel_offset))
+        ctx.mark_non_differentiable(area, dn)
+        return o, d, up, area, dn
+
+    @staticmethod
+    def backward(ctx, do, dd, dup, _da, _dn):
+        coords, c2w, intr, dist, pa = ctx.saved_tensors
+        n_pose, n_cam, off = ctx.cfg
+        if pa is None or not ctx.needs_input_grad[4]:
+            return None, None, None, None, None, None
+        dp = torch.zeros_like(pa)
+        do = _f(do) if do is not None else None
+        dd = _f(dd) if dd is not None else None
+        dup = _f(dup) if dup is not None else None
+        call("mmsb_raygen_bwd", ptr(coords), ptr(c2w), ptr(intr), ptr(dist), ptr(pa), _i32(n_pose), _i32(n_cam),
+             _f32(off), ptr(do), ptr(dd), ptr(dup), ptr(dp), _i64(coords.shape[0]), stream_ptr())
+        return None, None, None, None, dp, None
+
+
+def sphere_collide(origins, directions, radius=1.0, background=False):
+    """-> nears [n,1], fars [n,1], mask bool [n] (+ bg_nears, bg_fars when background=True). No grad."""
+    o, d = _rows(origins.detach(), 3), _rows(directions.detach(), 3)
+    n = o.shape[0]
+    nears = torch.empty((n, 1), device=o.device)
+    fars = torch.empty((n, 1), device=o.device)
+    mask = torch.empty((n,), device=o.device, dtype=torch.uint8)
+    bgn = torch.empty((n, 1), device=o.device) if background else None
+    bgf = torch.empty((n, 1), device=o.device) if background else None
+    call("mmsb_sphere_collide", ptr(o), ptr(d), _f32(radius), ptr(nears), ptr(fars), ptr(mask), ptr(bgn), ptr(bgf),
+         _i64(n), stream_ptr())
+    if background:
+        return nears, fars, mask, bgn, bgf
+    return nears, fars, mask
+
+
+# ------------------------------------------------------------------------------------------------
+# samplers (A4-A7), all no-grad
+# ------------------------------------------------------------------------------------------------
+_LIN_CACHE = {}
+
+
+def _linspace01(n_edges, device):
+    key = (n_edges, str(device))
+    if key not in _LIN_CACHE:
+        _LIN_CACHE[key] = torch.linspace(0.0, 1.0, n_edges).to(device)   # computed by torch on the CPU: same table as the reference
+    return _LIN_CACHE[key]
+
+
+def spaced_bins(nears, fars, num_samples, spacing, t_rand=None):
+    """-> spacing bins [n, S+1], euclidean bins [n, S+1]"""
+    nears, fars = _f(nears.detach()).reshape(-1), _f(fars.detach()).reshape(-1)
+    n = nears.shape[0]
+    lin = _linspace01(num_samples + 1, nears.device)
+    sb = torch.empty((n, num_samples + 1), device=nears.device)
+    eb = torch.empty_like(sb)
+    rpr = 0
+    if t_rand is not None:
+        t_rand = _f(t_rand)
+        rpr = t_rand.shape[-1]
+    call("mmsb_spaced_bins", ptr(nears), ptr(fars), ptr(lin), ptr(t_rand), _i32(rpr), _i32(num_samples), _i32(spacing),
+         ptr(sb), ptr(eb), _i64(n), stream_ptr())
+    return sb, eb
+
+
+def neus_upsample(bins, sdf, u, nears, fars, inv_s, histogram_padding=1e-5, eps=1e-5, want_debug=False):
+    bins, sdf, u = _f(bins), _f(sdf), _f(u)
+    nears, fars = _f(nears).reshape(-1), _f(fars).reshape(-1)
+    n, m = sdf.shape
+    k = u.shape[1] - 1
+    dev = bins.device
+    cdf = torch.empty((n, m + 1), device=dev)
+    inds = torch.empty((n, k + 1), device=dev, dtype=torch.int64) if want_debug else None
+    new_bins = torch.empty((n, k + 1), device=dev)
+    merged = torch.empty((n, m + k + 1), device=dev)
+    index = torch.empty((n, m + k), device=dev, dtype=torch.int64)
+    call("mmsb_neus_upsample", ptr(bins), ptr(sdf), ptr(u), ptr(nears), ptr(fars), _f32(inv_s), _f32(histogram_padding),
+         _f32(eps), _i32(m), _i32(k), ptr(cdf), ptr(inds), ptr(new_bins), ptr(merged), ptr(index), _i64(n), stream_ptr())
+    if want_debug:
+        return new_bins, merged, index, cdf, inds
+    return new_bins, merged, index
+
+
+def merge_rows(a, b, index):
+    a, b = _f(a), _f(b)
+    n, m = a.shape
+    k = b.shape[1]
+    out = torch.empty((n, m + k), device=a.device)
+    call("mmsb_merge_rows", ptr(a), _i32(m), ptr(b), _i32(k), ptr(index.contiguous()), ptr(out), _i64(n), stream_ptr())
+    return out
+
+
+def searchsorted_right(cdf, u):
+    cdf, u = _f(cdf), _f(u)
+    n, m = cdf.shape
+    q = u.shape[1]
+    inds = torch.empty((n, q), device=cdf.device, dtype=torch.int64)
+    call("mmsb_searchsorted_right", ptr(cdf), ptr(u), ptr(inds), _i32(m), _i32(q), _i64(n), stream_ptr())
+    return inds
+
+
+def pdf_inverse(cdf, bins, u):
+    cdf, bins, u = _f(cdf), _f(bins), _f(u)
+    n, nb = cdf.shape
+    q = u.shape[1]
+    inds = torch.empty((n, q), device=cdf.device, dtype=torch.int64)
+    out = torch.empty((n, q), device=cdf.device)
+    call("mmsb_pdf_inverse", ptr(cdf), ptr(bins), ptr(u), _i32(nb), _i32(q), ptr(inds), ptr(out), _i64(n), stream_ptr())
+    return inds, out
+
+
+# ------------------------------------------------------------------------------------------------
+# weights / compositing (A13, A14, A18, A19)
+# ------------------------------------------------------------------------------------------------
+class SdfTapsFn(torch.autograd.Function):
+    """(sdf_c [n], sdf_t [4,n]) -> gradients [n,3], hessians [n,3] or None, normals [n,3]"""
+
+    @staticmethod
+    def forward(ctx, sdf_c, sdf_t, delta, want_hessian):
+        sdf_c, sdf_t = _f(sdf_c).reshape(-1), _f(sdf_t).reshape(4, -1)
+        n = sdf_c.shape[0]
+        four_delta = float(np.float32(4.0 * delta))
+        delta_sq = float(np.float32(delta ** 2))
+        g = torch.empty((n, 3), device=sdf_c.device)
+        h = torch.empty((n, 3), device=sdf_c.device) if want_hessian else None
+        nrm = torch.empty((n, 3), device=sdf_c.device)
+        call("mmsb_sdf_taps_fwd", ptr(sdf_c), ptr(sdf_t), _f32(four_delta), _f32(delta_sq), ptr(g), ptr(h), ptr(nrm),
+             _i64(n), stream_ptr())
+        ctx.save_for_backward(sdf_t)
+        ctx.cfg = (four_delta, delta_sq, want_hessian)
+        if not want_hessian:
+            h = torch.zeros((0,), device=sdf_c.device)
+            ctx.mark_non_differentiable(h)
+        return g, h, nrm
+
+    @staticmethod
+    def backward(ctx, dg, dh, dn):
+        (sdf_t,) = ctx.saved_tensors
+        four_delta, delta_sq, want_hessian = ctx.cfg
+        n = sdf_t.shape[1]
+        d_c = torch.empty((n,), device=sdf_t.device)
+        d_t = torch.empty((4, n), device=sdf_t.device)
+        dg = _f(dg) if dg is not None else None
+        dh = _f(dh) if (dh is not None and want_hessian) else None
+        dn = _f(dn) if dn is not None else None
+        call("mmsb_sdf_taps_bwd", ptr(sdf_t), _f32(four_delta), _f32(delta_sq), ptr(dg), ptr(dh), ptr(dn), ptr(d_c),
+             ptr(d_t), _i64(n), stream_ptr())
+        return d_c, d_t, None, None
+
+
+class NeusWeightsFn(torch.autograd.Function):
+    """weights [n,s] from sdf [n,s], gradients [n,s,3], dirs [n,3], deltas [n,s], inv_s [1]."""
+
+    @staticmethod
+    def forward(ctx, sdf, grad, dirs, deltas, inv_s, mask, anneal):
+        n, s = sdf.shape[0], sdf.shape[1]
+        sdf, grad, dirs, deltas = _f(sdf).reshape(n, s), _f(grad).reshape(n, s, 3), _f(dirs).reshape(n, 3), _f(deltas).reshape(n, s)
+        inv_s = _f(inv_s).reshape(1)
+        w = torch.empty((n, s), device=sdf.device)
+        call("mmsb_neus_weights_fwd", ptr(sdf), ptr(grad), ptr(dirs), ptr(deltas), ptr(inv_s), ptr(mask), _f32(anneal),
+             ptr(w), _i32(s), _i64(n), stream_ptr())
+        ctx.save_for_backward(sdf, grad, dirs, deltas, inv_s, mask)
+        ctx.anneal = float(anneal)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        sdf, grad, dirs, deltas, inv_s, mask = ctx.saved_tensors
+        n, s = sdf.shape
+        dw = _f(dw).reshape(n, s)
+        d_sdf = torch.empty_like(sdf)
+        d_grad = torch.empty_like(grad)
+        d_dirs = torch.empty_like(dirs) if ctx.needs_input_grad[2] else None
+        d_deltas = torch.empty_like(deltas) if ctx.needs_input_grad[3] else None
+        d_inv_s = torch.zeros_like(inv_s)
+        call("mmsb_neus_weights_bwd", ptr(sdf), ptr(grad), ptr(dirs), ptr(deltas), ptr(inv_s), ptr(mask),
+             _f32(ctx.anneal), ptr(dw), ptr(d_sdf), ptr(d_grad), ptr(d_dirs), ptr(d_deltas), ptr(d_inv_s), _i32(s),
+             _i64(n), stream_ptr())
+        return d_sdf, d_grad, d_dirs, d_deltas, d_inv_s, None, None
+
+
+class DensityWeightsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, density, deltas):
+        n, s = density.shape[0], density.shape[1]
+        density, deltas = _f(density).reshape(n, s), _f(deltas).reshape(n, s)
+        w = torch.empty((n, s), device=density.device)
+        call("mmsb_density_weights_fwd", ptr(density), ptr(deltas), ptr(w), _i32(s), _i64(n), stream_ptr())
+        ctx.save_for_backward(density, deltas)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        density, deltas = ctx.saved_tensors
+        n, s = density.shape
+        dd = torch.empty_like(density)
+        ddel = torch.empty_like(deltas) if ctx.needs_input_grad[1] else None
+        call("mmsb_density_weights_bwd", ptr(density), ptr(deltas), ptr(_f(dw).reshape(n, s)), ptr(dd), ptr(ddel),
+             _i32(s), _i64(n), stream_ptr())
+        return dd, ddel
+
+
+class CompositeFn(torch.autograd.Function):
+    """color [n,c] = sum_s w v + bg (1 - sum_s w)"""
+
+    @staticmethod
+    def forward(ctx, weights, values, background):
+        n, s = weights.shape[0], weights.shape[1]
+        c = values.shape[-1]
+        weights, values = _f(weights).reshape(n, s), _f(values).reshape(n, s, c)
+        background = _f(background).reshape(n, c) if background is not None else None
+        out = torch.empty((n, c), device=weights.device)
+        call("mmsb_composite_fwd", ptr(weights), ptr(values), ptr(background), _i32(c), None, None, None, ptr(out),
+             None, None, None, _i32(s), _i64(n), stream_ptr())
+        ctx.save_for_backward(weights, values, background)
+        return out
+
+    @staticmethod
+    def backward(ctx, dc):
+        weights, values, background = ctx.saved_tensors
+        n, s = weights.shape
+        c = values.shape[-1]
+        dw = torch.empty_like(weights)
+        dv = torch.empty_like(values) if ctx.needs_input_grad[1] else None
+        dbg = torch.empty_like(background) if (background is not None and ctx.needs_input_grad[2]) else None
+        call("mmsb_composite_bwd", ptr(weights), ptr(values), ptr(background), _i32(c), ptr(_f(dc).reshape(n, c)), None,
+             None, None, None, None, None, ptr(dw), ptr(dv), ptr(dbg), None, _i32(s), _i64(n), stream_ptr())
+        return dw, dv, dbg
+
+
+def composite_aux(weights, normals, starts, ends):
+    """No-grad diagnostics: rendered normals [n,3], unclipped depth [n,1], accumulation [n,1]."""
+    n, s = weights.shape[0], weights.shape[1]
+    weights = _f(weights.detach()).reshape(n, s)
+    normals = _f(normals.detach()).reshape(n, s, 3)
+    starts, ends = _f(starts.detach()).reshape(n, s), _f(ends.detach()).reshape(n, s)
+    on = torch.empty((n, 3), device=weights.device)
+    od = torch.empty((n, 1), device=weights.device)
+    oa = torch.empty((n, 1), device=weights.device)
+    call("mmsb_composite_fwd", ptr(weights), None, None, _i32(0), ptr(normals), ptr(starts), ptr(ends), None, ptr(on),
+         ptr(od), ptr(oa), _i32(s), _i64(n), stream_ptr())
+    return on, od, oa
+
+
+# ------------------------------------------------------------------------------------------------
+# losses (A21, A22)
+# ------------------------------------------------------------------------------------------------
+def first_saturated(target, threshold):
+    t = _f(target.detach()).reshape(-1)
+    idx = torch.empty((1,), device=t.device, dtype=torch.int64)
+    call("mmsb_first_saturated", ptr(t), _f32(threshold), ptr(idx), _i64(t.numel()), stream_ptr())
+    return idx
+
+
+class MosaickL1Fn(torch.autograd.Function):
+    """mean |select(rendered) - target| with the mosaick band select fused (pattern may be None)."""
+
+    @staticmethod
+    def forward(ctx, rendered, target, coords, pattern, ph, pw, sat_threshold, sat_index):
+        n, c = rendered.shape
+        rendered = _f(rendered)
+        target = _f(target.detach())
+        coords = coords.to(torch.int32).contiguous() if coords is not None else None
+        count = n if pattern is not None else n * c
+        loss = torch.zeros((1,), device=rendered.device)
+        sel = torch.empty((n,), device=rendered.device) if pattern is not None else None
+        call("mmsb_mosaick_l1_fwd", ptr(coords), ptr(pattern), _i32(ph), _i32(pw), ptr(rendered), _i32(c), ptr(target),
+             _f32(sat_threshold), ptr(sat_index), None, ptr(sel), ptr(loss), _i64(n), stream_ptr())
+        ctx.save_for_backward(rendered, target, coords, pattern, sat_index)
+        ctx.cfg = (ph, pw, float(sat_threshold), 1.0 / max(count, 1))
+        out = (loss / max(count, 1)).reshape(())
+        if sel is None:
+            sel = torch.zeros((0,), device=rendered.device)
+        ctx.mark_non_differentiable(sel)
+        return out, sel
+
+    @staticmethod
+    def backward(ctx, dloss, _dsel):
+        rendered, target, coords, pattern, sat_index = ctx.saved_tensors
+        ph, pw, thr, inv_count = ctx.cfg
+        n, c = rendered.shape
+        dr = torch.empty_like(rendered)
+        dl = _f(dloss).reshape(1)
+        call("mmsb_mosaick_l1_bwd", ptr(coords), ptr(pattern), _i32(ph), _i32(pw), ptr(rendered), _i32(c), ptr(target),
+             _f32(thr), ptr(sat_index), ptr(dl), _f32(inv_count), ptr(dr), _i64(n), stream_ptr())
+        return dr, None, None, None, None, None, None, None
+
+
+def mosaick_bands(coords, pattern, ph, pw, rendered):
+    """band int64 [n] and the gathered channel [n] (index-parity surface; A21)."""
+    n, c = rendered.shape
+    rendered = _f(rendered.detach())
+    coords = coords.to(torch.int32).contiguous()
+    band = torch.empty((n,), device=rendered.device, dtype=torch.int64)
+    sel = torch.empty((n,), device=rendered.device)
+    loss = torch.zeros((1,), device=rendered.device)
+    tgt = torch.zeros((n,), device=rendered.device)
+    call("mmsb_mosaick_l1_fwd", ptr(coords), ptr(pattern), _i32(ph), _i32(pw), ptr(rendered), _i32(c), ptr(tgt),
+         _f32(float("inf")), None, ptr(band), ptr(sel), ptr(loss), _i64(n), stream_ptr())
+    return band, sel
+
+
+class GeometryLossFn(torch.autograd.Function):
+    """(eikonal, curvature) means over the unmasked samples of gradients/hessians [n,s,3]."""
+
+    @staticmethod
+    def forward(ctx, gradients, hessians, ray_mask):
+        nr, s = gradients.shape[0], gradients.shape[1]
+        g = _f(gradients).reshape(nr * s, 3)
+        h = _f(hessians).reshape(nr * s, 3) if hessians is not None else None
+        sums = torch.zeros((3,), device=g.device)
+        call("mmsb_geometry_loss_fwd", ptr(g), ptr(h), ptr(ray_mask), _i32(s), ptr(sums), _i64(nr * s), stream_ptr())
+        ctx.save_for_backward(g, h, ray_mask, sums)
+        ctx.cfg = (s, gradients.shape)
+        cnt = sums[2].clamp_min(1.0)
+        return sums[0] / cnt, sums[1] / cnt
+
+    @staticmethod
+    def backward(ctx, d_eik, d_curv):
+        g, h, ray_mask, sums = ctx.saved_tensors
+        s, shape = ctx.cfg
+        dg = torch.empty_like(g)
+        dh = torch.empty_like(h) if h is not None else None
+        de = _f(d_eik).reshape(1) if d_eik is not None else None
+        dc = _f(d_curv).reshape(1) if d_curv is not None else None
+        call("mmsb_geometry_loss_bwd", ptr(g), ptr(h), ptr(ray_mask), _i32(s), ptr(sums), ptr(de), ptr(dc), ptr(dg),
+             ptr(dh), _i64(g.shape[0]), stream_ptr())
+        return dg.reshape(shape), (dh.reshape(shape) if dh is not None else None), None
+
+
+# ------------------------------------------------------------------------------------------------
+# optimiser (A23, "next" row 1)
+# ------------------------------------------------------------------------------------------------
+def sumsq(x, out):
+    call("mmsb_sumsq", ptr(x), ptr(out), _i64(x.numel()), stream_ptr())
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, grad_scale, lr, beta1, beta2, eps, weight_decay, step):
+    call("mmsb_adamw_step", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(grad_scale), _f32(lr), _f32(beta1),
+         _f32(beta2), _f32(eps), _f32(weight_decay), _i32(step), _i64(param.numel()), stream_ptr())
