@@ -146,6 +146,32 @@ def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_timed = None      # set of entry points to bracket with CUDA events (bench.py roofline pass), else None
+_records = []
+
+
+def start_kernel_timing(names):
+    global _timed, _records
+    _timed, _records = set(names), []
+
+
+def stop_kernel_timing():
+    """-> [(name, milliseconds, args)] for every instrumented call since start_kernel_timing (caller synchronised)."""
+    global _timed
+    _timed = None
+    return [(n, s.elapsed_time(e), a) for n, s, e, a in _records]
+
+
 def call(name: str, *args):
     lib = load_library()
+    if _timed is not None and name in _timed:
+        import torch
+
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = getattr(lib, name)(*args)
+        e.record()
+        _records.append((name, s, e, args))
+        check(rc, name)
+        return
     check(getattr(lib, name)(*args), name)

@@ -1,0 +1,205 @@
+"""Mirror of the reference's pipeline step for the hot path: ray generation -> BaseModel.forward ->
+mosaick channel select + losses -> backward -> global-norm clip -> AdamW.
+ref: src/pipelines/raw_pipeline.py:67-82,112-122, src/pipelines/base_pipeline.py:139-153,232-248,
+     src/engine/optimizers.py:96-116, src/engine/schedulers.py:249-270, src/engine/trainer.py:86-138
+
+The synthetic scene generator follows SURVEY.md §8(d) (no dataset is available offline).
+"""
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .cameras import CameraOptimizer, CameraOptimizerConfig, Cameras, RayGenerator
+from .configs import TrainingCallbackAttributes, TrainingCallbackLocation
+from .models import MODALITY_CHANNELS, MOSAICK_PATTERNS, build_model, grid_loss_config
+
+# per-modality image geometry: (width, height, focal)
+MODALITY_SENSORS = {
+    "rgb": (2448, 2048, 2400.0), "infrared": (1224, 1024, 1200.0), "mono": (1224, 1024, 1200.0),
+    "polarization": (2448, 2048, 2400.0), "multispectral": (1269, 981, 1250.0),
+}
+
+
+def select_right_channel_per_pixel(pixel_coords_per_modality, outputs, modalities=None, patterns=None):
+    """ref: raw_pipeline.py:112-122 — `outputs[mod][mod] [R,C] -> [R,1]` with band = pattern[y % ph, x % pw].
+    (The training step does not call this: the select is fused into the loss kernel.)"""
+    patterns = patterns or MOSAICK_PATTERNS
+    for mod in (modalities or outputs.keys()):
+        pat = torch.tensor(patterns[mod], dtype=torch.int32, device=outputs[mod][mod].device)
+        _, sel = ops.mosaick_bands(pixel_coords_per_modality[mod], pat.reshape(-1), pat.shape[0], pat.shape[1],
+                                   outputs[mod][mod])
+        outputs[mod][mod] = sel[:, None]
+    return outputs
+
+
+def look_at_cameras(n_cam: int, radius: float, seed: int, offset=None) -> torch.Tensor:
+    """n_cam camera-to-world matrices [n,3,4] on a shell of `radius`, looking at the origin (+ jitter),
+    OpenGL convention (camera looks down -z, +y up) like the reference's ray generation."""
+    g = torch.Generator().manual_seed(seed)
+    pos = torch.nn.functional.normalize(torch.randn(n_cam, 3, generator=g), dim=-1) * radius
+    fwd = torch.nn.functional.normalize(-pos + 0.05 * torch.randn(n_cam, 3, generator=g), dim=-1)
+    helper = torch.tensor([0.0, 0.0, 1.0]).expand(n_cam, 3)
+    right = torch.nn.functional.normalize(torch.linalg.cross(fwd, helper), dim=-1)
+    up = torch.linalg.cross(right, fwd)
+    c2w = torch.cat([torch.stack([right, up, -fwd], -1), pos[..., None]], -1)
+    if offset is not None:   # camera2reference folded into camtoworld offline (preprocessing/utils.py:531-548)
+        rot, t = offset
+        c2w = torch.cat([c2w[:, :, :3] @ rot, c2w[:, :, 3:] + c2w[:, :, :3] @ t[:, None]], -1)
+    return c2w
+
+
+class SyntheticScene:
+    """Cameras, pixel coordinates and targets of the synthetic workload."""
+
+    def __init__(self, modalities: Dict[str, int], rays_per_modality: Dict[str, int], n_cam: int = 50, seed: int = 654824,
+                 raw: bool = True):
+        self.modalities, self.rays, self.raw = modalities, rays_per_modality, raw
+        self.cameras = {}
+        for i, mod in enumerate(modalities):
+            w, h, f = MODALITY_SENSORS[mod]
+            ang = 0.01 * (i + 1)
+            rot = torch.tensor([[math.cos(ang), -math.sin(ang), 0.0], [math.sin(ang), math.cos(ang), 0.0], [0.0, 0.0, 1.0]])
+            c2w = look_at_cameras(n_cam, 2.5, seed + 17, offset=(rot, torch.tensor([0.02 * i, -0.01 * i, 0.0])))
+            dist = torch.tensor([-0.1, 0.01, 0.0, 0.0, 1e-3, -1e-3]).expand(n_cam, 6).contiguous()
+            self.cameras[mod] = Cameras(c2w, f, f, w / 2.0, h / 2.0, width=w, height=h, distortion_params=dist)
+        self.n_cam = n_cam
+        self.gen = torch.Generator().manual_seed(seed)     # trainer.py:64 / pixel_samplers.py:52 (+ rank offset by the caller)
+
+    def sample_batch(self):
+        """UniformPixelSampler semantics (pixel_samplers.py:71-89): CPU randint per modality -> coords int32 [R,3]
+        (cam, y, x) and synthetic targets."""
+        coords, targets = {}, {}
+        for mod, c in self.modalities.items():
+            w, h, _ = MODALITY_SENSORS[mod]
+            r = self.rays[mod]
+            coords[mod] = torch.stack([torch.randint(0, self.n_cam, (r,), generator=self.gen),
+                                       torch.randint(0, h, (r,), generator=self.gen),
+                                       torch.randint(0, w, (r,), generator=self.gen)], -1).int()
+            t = torch.rand(r, 1 if self.raw else c, generator=self.gen)
+            if mod == "polarization":
+                t[torch.rand(r, generator=self.gen) < 0.005] = 1.0       # exercise skip-saturation
+            targets[mod] = t
+        return coords, targets
+
+
+class FlatAdamW:
+    """One AdamW "optimizer" of the reference (engine/optimizers.py, method_configs.py:260-269) over a flat
+    fp32 buffer: parameters and gradients are views into two contiguous tensors, so zero-grad is one memset,
+    the global-norm clip one reduction, the update one fused kernel and the DDP all-reduce one NCCL call."""
+
+    def __init__(self, params: List[torch.nn.Parameter], lr=1e-3, weight_decay=0.01, eps=1e-15, betas=(0.9, 0.999),
+                 max_norm: Optional[float] = 2.0):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.empty(n, device=dev)
+        self.grad = torch.zeros(n, device=dev)
+        self.exp_avg = torch.zeros(n, device=dev)
+        self.exp_avg_sq = torch.zeros(n, device=dev)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p)
+            p.grad = self.grad[off:off + k].view_as(p)
+            off += k
+        self.lr, self.wd, self.eps, self.betas, self.max_norm = lr, weight_decay, eps, betas, max_norm
+        self.step_count = 0
+        self.sumsq = torch.zeros(1, device=dev)
+        self.scale = torch.ones(1, device=dev)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def step(self, lr_factor: float = 1.0):
+        self.step_count += 1
+        scale = None
+        if self.max_norm is not None:
+            # clip_grad_norm_(max_norm, error_if_nonfinite=False): coef = max_norm / (norm + 1e-6), clamped to 1
+            self.sumsq.zero_()
+            ops.sumsq(self.grad, self.sumsq)
+            torch.clamp(self.max_norm / (self.sumsq.sqrt() + 1e-6), max=1.0, out=self.scale)
+            scale = self.scale
+        ops.adamw_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, scale, self.lr * lr_factor, self.betas[0],
+                       self.betas[1], self.eps, self.wd, self.step_count)
+
+
+def multistep_warmup_factor(step, num_iterations, warm_up_ratio=0.1, milestones=(0.5, 0.75, 0.9), gamma=0.4):
+    """ref: engine/schedulers.py:249-270"""
+    warm_up_end = int(num_iterations * warm_up_ratio)
+    if step < warm_up_end:
+        return step / warm_up_end
+    return gamma ** int(np.searchsorted(milestones, step / num_iterations, side="left"))
+
+
+class RawPipeline:
+    """train_step of the reference's RawPipeline / BasePipeline on the B200 path.
+    `raw=True`: mosaicked frames (grid_raw); `raw=False`: demosaicked (grid)."""
+
+    def __init__(self, modalities: Dict[str, int], cameras: Dict[str, Cameras], device="cuda", raw=True,
+                 max_num_iterations=100000, pose_mode="SO3xR3", shared_pose=True, render_all_heads=False,
+                 process_group=None, **model_kwargs):
+        self.device, self.raw, self.modalities = torch.device(device), raw, modalities
+        self.max_num_iterations = max_num_iterations
+        self.model = build_model("grid_raw" if raw else "grid", modalities=modalities, render_all_heads=render_all_heads,
+                                 **model_kwargs).to(self.device)
+        n_cam = len(next(iter(cameras.values())))
+        self.camera_optimizer = CameraOptimizerConfig(mode=pose_mode, shared_optimization=shared_pose,
+                                                      modalities_to_optimize={m: True for m in modalities}
+                                                      ).setup(num_cameras=n_cam).to(self.device)
+        self.ray_generator = RayGenerator({m: {"cameras": c.to(self.device)} for m, c in cameras.items()},
+                                          self.camera_optimizer, pixel_offset=0.0)
+        self.loss_manager = grid_loss_config().setup(modalities=list(modalities), num_iterations=max_num_iterations,
+                                                     model=self.model)
+        self.patterns = {m: torch.tensor(MOSAICK_PATTERNS[m], dtype=torch.int32, device=self.device) for m in modalities} if raw else None
+        self.optimizers = {"fields": FlatAdamW(list(self.model.parameters()), lr=1e-3)}
+        pose_params = list(self.camera_optimizer.parameters())
+        if pose_params:
+            self.optimizers["camera_poses"] = FlatAdamW(pose_params, lr=1e-4)
+
+        class _T:
+            pass
+        t = _T(); t.max_num_iterations = max_num_iterations
+        self.callbacks = self.model.get_training_callbacks(TrainingCallbackAttributes(model=self.model, trainer=t))
+        self.process_group = process_group
+        self.model.train()
+
+    def run_callbacks(self, step):
+        for cb in self.callbacks:
+            cb.run_callback_at_location(step, TrainingCallbackLocation.BEFORE_TRAIN_ITERATION)
+
+    def forward_backward(self, coords, targets, step):
+        ray_bundles = self.ray_generator(coords)
+        outputs = self.model(ray_bundles)
+        losses, total = self.loss_manager.compute_loss(outputs, targets, coords, step, mosaick_patterns=self.patterns)
+        for opt in self.optimizers.values():
+            opt.zero_grad()
+        total.backward()
+        return losses, total
+
+    def all_reduce_gradients(self):
+        """DDP semantics of the reference (mean over ranks) — one flat NCCL all-reduce per optimizer."""
+        import torch.distributed as dist
+        if self.process_group is None and not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        ws = dist.get_world_size(self.process_group)
+        for opt in self.optimizers.values():
+            dist.all_reduce(opt.grad, op=dist.ReduceOp.SUM, group=self.process_group)
+            opt.grad.mul_(1.0 / ws)
+
+    def optimizer_step(self, step):
+        f = multistep_warmup_factor(step, self.max_num_iterations)
+        for opt in self.optimizers.values():
+            opt.step(lr_factor=f)
+
+    def train_step(self, step, coords, targets):
+        """coords {mod: int32 [R,3]}, targets {mod: [R,1] raw or [R,C]} — already on the device."""
+        self.run_callbacks(step)
+        losses, total = self.forward_backward(coords, targets, step)
+        self.all_reduce_gradients()
+        self.optimizer_step(step)
+        return losses, total

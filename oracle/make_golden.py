@@ -154,6 +154,7 @@ def golden_samplers():
     cdf = torch.cumsum(torch.rand(30, 20, generator=g), -1)
     cdf = torch.cat([torch.zeros(30, 1), cdf / cdf[:, -1:]], -1)
     cdf[0, :5] = torch.tensor([0, .2, .2, .7, 1.0])
+    cdf[0, 5:] = 1.0
     u = torch.rand(30, 9, generator=g)
     u[0, :5] = torch.tensor([0, .2, .69999, .7, 1.0])
     u[1, :3] = cdf[1, 3:6]                                    # exact hits
@@ -359,6 +360,10 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     import_reference()
+    if len(sys.argv) > 1:
+        for name in sys.argv[1:]:
+            globals()["golden_" + name]()
+        sys.exit(0)
     golden_hashgrid()
     golden_encodings()
     golden_mlp()

@@ -1,0 +1,58 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+class Golden(dict):
+    """npz fixture produced by oracle/make_golden.py from the unmodified reference."""
+
+    def t(self, key, device="cpu"):
+        v = torch.from_numpy(np.asarray(self[key]))
+        return v.to(device)
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
+        return Golden({k: z[k] for k in z.files})
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return load_golden
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def assert_close(a, b, rtol=1e-5, atol=None, what=""):
+    """max |a-b| <= rtol * max|b| (+ atol): the 1e-5 relative fp32 band of BASELINE.json."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    tol = rtol * float(b.abs().max()) + (atol or 0.0)
+    err = float((a - b).abs().max()) if a.numel() else 0.0
+    assert err <= tol, f"{what}: max abs err {err:.3e} > tol {tol:.3e} (rtol {rtol})"

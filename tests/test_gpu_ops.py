@@ -1,0 +1,377 @@
+"""GPU parity, operator by operator, through the C ABI (libmms_b200.so via ctypes):
+ (1) against the fixtures generated from the unmodified reference (tests/golden), and
+ (2) against the CPU oracle on seeded inputs at larger sizes.
+Integer / index outputs must be bit-exact; floats within 1e-5 relative (BASELINE.json)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import mms_oracle as O
+from conftest import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ops():
+    from multimodalstudio_b200 import ops
+    return ops
+
+
+def _table(seed, log2, levels=16, feats=2):
+    torch.manual_seed(seed)
+    return (torch.rand((2 ** log2) * levels, feats) * 2 - 1) * 0.001
+
+
+# ---------------------------------------------------------------- hash grid (A9/A10)
+def test_hashgrid_golden():
+    ops = _ops()
+    g = load_golden("hashgrid")
+    table = _table(int(g["table_seed"]), 10).to(DEV).requires_grad_(True)
+    desc = ops.make_hashgrid_desc(16, 2, 10, g["resolutions"].tolist())
+    x = g.t("x", DEV).requires_grad_(True)
+    idx, _ = ops.hashgrid_indices(desc, x.detach(), table.detach())
+    assert torch.equal(idx.cpu(), g.t("indices").long())                       # bit-exact indices
+    feats = ops.HashGridFn.apply(x, table, None, desc)
+    assert_close(feats, g.t("features"), rtol=1e-6, what="features")
+    assert torch.equal(feats.detach().cpu(), g.t("features")), "features are IEEE-reproducible bit for bit"
+    (feats * g.t("cotangent", DEV)).sum().backward()
+    assert_close(table.grad, g.t("dtable"), what="dtable")
+    assert_close(x.grad, g.t("dx"), what="dx")
+    # FeatureGrid: rescale + coarse-to-fine mask fused
+    mask = torch.ones(32, device=DEV)
+    mask[int(g["fg_level"]) * 2:] = 0
+    d1 = ops.make_hashgrid_desc(16, 2, 10, g["resolutions"].tolist(), radius=1.0)
+    fg = ops.HashGridFn.apply(g.t("fg_x", DEV), table.detach(), mask, d1)
+    assert_close(fg, g.t("fg_features"), rtol=1e-6, what="feature grid")
+
+
+@pytest.mark.parametrize("n,log2", [(0, 12), (1, 12), (1000, 12), (200_003, 19)])
+def test_hashgrid_vs_oracle(n, log2):
+    ops = _ops()
+    table = _table(3, log2)
+    res = O.hash_resolutions(16, 1024, 16)
+    gen = torch.Generator().manual_seed(n + 1)
+    x = torch.rand(n, 3, generator=gen) * 2.2 - 1.1
+    mask = torch.ones(32); mask[20:] = 0
+    desc = ops.make_hashgrid_desc(16, 2, log2, res.tolist(), radius=1.0)
+    xg, tg = x.to(DEV).requires_grad_(True), table.to(DEV).requires_grad_(True)
+    out = ops.HashGridFn.apply(xg, tg, mask.to(DEV), desc)
+    assert out.shape == (n, 32)
+    if n == 0:
+        return
+    nchk = min(n, 20000)
+    xo, to = x[:nchk].clone().requires_grad_(True), table.clone().requires_grad_(True)
+    ref = O.hash_encode(xo, to, res, log2, radius=1.0, mask=mask)
+    assert torch.equal(out[:nchk].detach().cpu(), ref.detach()), "bit-exact features"
+    idx, _ = ops.hashgrid_indices(ops.make_hashgrid_desc(16, 2, log2, res.tolist()), ((xg.detach() + 1) / 2)[:nchk], tg.detach())
+    assert torch.equal(idx.cpu(), O.hash_indices((x[:nchk] + 1.0) / 2.0, res, log2)[0])
+    cot = torch.randn(nchk, 32, generator=gen)
+    (ref * cot).sum().backward()
+    full = torch.zeros(n, 32); full[:nchk] = cot
+    (out * full.to(DEV)).sum().backward()
+    assert_close(tg.grad, to.grad, rtol=2e-5, what="dtable")
+    assert_close(xg.grad[:nchk], xo.grad, rtol=2e-5, what="dx")
+
+
+def test_hashgrid_linearity_full_size():
+    """size-independent property at the shipped table size: the encoding is linear in the table."""
+    ops = _ops()
+    res = O.hash_resolutions(16, 1024, 16).tolist()
+    desc = ops.make_hashgrid_desc(16, 2, 19, res, radius=1.0)
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.rand(300_000, 3, device=DEV, generator=gen) * 2 - 1
+    t1 = torch.randn((2 ** 19) * 16, 2, device=DEV, generator=gen)
+    t2 = torch.randn((2 ** 19) * 16, 2, device=DEV, generator=gen)
+    f = lambda t: ops.HashGridFn.apply(x, t, None, desc)
+    assert_close(f(t1 + 2 * t2), f(t1) + 2 * f(t2), rtol=1e-5, what="linearity")
+    # checksum of the scatter: sum(dtable) == sum over points of sum_corner weights * cotangent = sum(cot)
+    t = t1.clone().requires_grad_(True)
+    f(t).sum().backward()
+    assert abs(float(t.grad.double().sum()) - 300_000 * 32) < 1e-3 * 300_000 * 32
+
+
+# ---------------------------------------------------------------- encodings (A8/A15)
+def test_encodings_golden():
+    ops = _ops()
+    g = load_golden("encodings")
+    x = g.t("x", DEV).requires_grad_(True)
+    y6 = ops.NerfEncodingFn.apply(x, ops.nerf_freqs(0.0, 5, 6), True)
+    assert_close(y6, g.t("pe6"), rtol=2e-6)
+    assert_close(ops.NerfEncodingFn.apply(x, ops.nerf_freqs(0.0, 3, 4), True), g.t("pe4"), rtol=2e-6)
+    (y6 * g.t("cot6", DEV)).sum().backward()
+    assert_close(x.grad, g.t("dx6"))
+    d = g.t("dirs", DEV).requires_grad_(True)
+    sh = ops.SHEncodingFn.apply(d, 5)
+    assert_close(sh, g.t("sh5"), rtol=2e-6)
+    do = g.t("dirs").requires_grad_(True)
+    cot = torch.randn(64, 25, generator=torch.Generator().manual_seed(1))
+    (O.sh_encode(5, do) * cot).sum().backward()
+    (sh * cot.to(DEV)).sum().backward()
+    assert_close(d.grad, do.grad)
+
+
+# ---------------------------------------------------------------- MLP (A11)
+@pytest.mark.parametrize("name,cfgkw,din,dout", [
+    ("sdf", dict(num_layers=3, hidden_dim=48, activation="Softplus", activation_params={"beta": 100}, out_activation="None",
+                 geometric_init=True, geometric_init_bias=0.4, weight_norm=True), 23, 20),
+    ("rad", dict(num_layers=3, hidden_dim=40, out_activation="ReLU", weight_norm=True), 37, 24),
+    ("head", dict(num_layers=3, hidden_dim=16, out_activation="Sigmoid", weight_norm=True), 24, 9),
+    ("dens", dict(num_layers=1, hidden_dim=64, weight_norm=True, out_activation="Softplus"), 24, 1),
+])
+def test_mlp_golden(name, cfgkw, din, dout):
+    from multimodalstudio_b200.field_components import MLPConfig
+    g = load_golden("mlp")
+    torch.manual_seed(int(g["seed"]))
+    m = MLPConfig(**cfgkw).setup(input_dim=din, output_dim=dout).to(DEV)
+    x = g.t(name + "_x", DEV).requires_grad_(True)
+    y = m(x)
+    assert_close(y, g.t(name + "_y"), what="y")
+    (y * g.t(name + "_cot", DEV)).sum().backward()
+    assert_close(x.grad, g.t(name + "_dx"), what="dx")
+    for k, p in m.named_parameters():
+        assert_close(p.grad, g.t(f"{name}_grad.{k}"), rtol=2e-5, atol=1e-9, what=k)
+
+
+@pytest.mark.parametrize("n", [1, 127, 4099])
+def test_mlp_shapes_vs_oracle(n):
+    """the shipped layer shapes (SDF 71->256->256->257 softplus; radiance 319->256->256->256 relu), ragged n."""
+    from multimodalstudio_b200.field_components import MLPConfig
+    for din, dout, kw, acts in [
+        (71, 257, dict(num_layers=3, hidden_dim=256, activation="Softplus", activation_params={"beta": 100},
+                       out_activation="None", geometric_init=True, geometric_init_bias=0.4), ("Softplus", "None", 100.0)),
+        (319, 256, dict(num_layers=3, hidden_dim=256, out_activation="ReLU"), ("ReLU", "ReLU", 1.0)),
+    ]:
+        torch.manual_seed(5)
+        m = MLPConfig(weight_norm=True, **kw).setup(input_dim=din, output_dim=dout)
+        sd = {("f." + k): v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+        gen = torch.Generator().manual_seed(n)
+        x = torch.randn(n, din, generator=gen) * 0.3
+        xo = x.clone().requires_grad_(True)
+        ref = O.mlp(sd, "f", xo, 3, acts[0], acts[1], acts[2])
+        cot = torch.randn(ref.shape, generator=gen)
+        (ref * cot).sum().backward()
+        mg = m.to(DEV)
+        xg = x.to(DEV).requires_grad_(True)
+        y = mg(xg)
+        assert_close(y, ref, what="y")
+        (y * cot.to(DEV)).sum().backward()
+        assert_close(xg.grad, xo.grad, rtol=2e-5, what="dx")
+        for k, p in mg.named_parameters():
+            assert_close(p.grad, sd["f." + k].grad, rtol=3e-5, atol=1e-8, what=k)
+        # sdf-only evaluation == first output column
+        if dout == 257:
+            assert_close(mg(xg.detach(), n_out_used=1), ref[:, :1].detach(), what="sdf only")
+
+
+# ---------------------------------------------------------------- samplers (A3-A7)
+def test_samplers_golden():
+    ops = _ops()
+    g = load_golden("samplers")
+    o, d = g.t("origins", DEV), g.t("directions", DEV)
+    nears, fars, mask, bgn, bgf = ops.sphere_collide(o, d, 1.0, True)
+    assert torch.equal(mask.cpu().bool(), g.t("mask"))
+    assert torch.equal(nears.cpu(), g.t("nears")) and torch.equal(fars.cpu(), g.t("fars"))       # bit-exact
+    bn, bf = O.background_near_far(g.t("nears"), g.t("fars"), g.t("mask"))
+    assert torch.equal(bgn.cpu(), bn) and torch.equal(bgf.cpu(), bf)
+    for tag, ns, sp in (("uni", 32, ops.SPACING_UNIFORM), ("disp", 16, ops.SPACING_DISPARITY)):
+        sb, eb = ops.spaced_bins(nears, fars, ns, sp, None)
+        assert torch.equal(sb.cpu(), g.t(tag + "_eval_sbins")) and torch.equal(eb.cpu(), g.t(tag + "_eval_ebins"))
+        sb, eb = ops.spaced_bins(nears, fars, ns, sp, g.t(tag + "_rand", DEV))
+        assert torch.equal(sb.cpu(), g.t(tag + "_train_sbins")), "sample bins bit-exact"
+        assert torch.equal(eb.cpu(), g.t(tag + "_train_ebins"))
+    inds = ops.searchsorted_right(g.t("ss_cdf", DEV), g.t("ss_u", DEV))
+    assert torch.equal(inds.cpu(), g.t("ss_inds")), "searchsorted bit-exact"
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_neus_sampler_golden(mode):
+    """NeuSSampler end to end (4 up-sampling rounds) with the analytic sdf the fixture used."""
+    from multimodalstudio_b200.cameras import RayBundle
+    from multimodalstudio_b200.model_components import NeuSSamplerConfig
+    ops = _ops()
+    g = load_golden("samplers")
+    o, d = g.t("origins", DEV), g.t("directions", DEV)
+    rb = RayBundle(camera_indices=None, origins=o, directions=d, up_directions=d)
+    rb.nears, rb.fars, _ = ops.sphere_collide(o, d, 1.0)
+
+    def sdf_fn(samples):
+        p = samples.frustums.get_start_positions()
+        return p.norm(dim=-1, keepdim=True) - 0.6 + 0.02 * torch.sin(9.0 * p[..., 0:1])
+
+    neus = NeuSSamplerConfig(num_samples=32, num_samples_importance=32).setup()
+    neus.train(mode == "train")
+    rand = {"uniform": {"m": g.t("neus_rand_uniform", DEV)}, "pdf": {"m": list(g.t("neus_rand_pdf", DEV))}} if mode == "train" else None
+    s = neus({"m": rb}, sdf_fn=sdf_fn, rand=rand)["ray_samples_per_modality"]["m"]
+    sb = torch.cat([s.spacing_starts[..., 0], s.spacing_ends[..., -1:, 0]], -1)
+    assert sb.shape == (o.shape[0], 65)
+    assert bool((sb[:, 1:] >= sb[:, :-1]).all()), "bins sorted"
+    assert_close(sb, g.t(f"neus_{mode}_sbins"), rtol=2e-6, what="neus bins")
+
+
+@pytest.mark.parametrize("n,m,k", [(1, 32, 8), (333, 40, 8), (5000, 56, 8), (64, 128, 32)])
+def test_upsample_round_vs_oracle(n, m, k):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(n * 7 + m)
+    nears = torch.rand(n, 1, generator=gen) + 1.0
+    fars = nears + 1.0 + torch.rand(n, 1, generator=gen)
+    bins = torch.sort(torch.rand(n, m + 1, generator=gen), -1)[0]
+    bins[:, 0], bins[:, -1] = 0.0, 1.0
+    t = O.spacing_to_euclid(bins[:, :-1], nears, fars)
+    sdf = (2.0 - t) * 0.5 + 0.01 * torch.randn(n, m, generator=gen)
+    u = O.make_u(n, k, torch.rand(n, 1, generator=gen))
+    ref = O.upsample_round(bins, sdf, u, nears, fars, 64.0 * 4)
+    new_bins, merged, index, cdf, inds = ops.neus_upsample(bins.to(DEV), sdf.to(DEV), u.to(DEV), nears.to(DEV), fars.to(DEV),
+                                                           inv_s=256.0, want_debug=True)
+    assert_close(cdf, ref["cdf"], rtol=2e-6, what="cdf")
+    # the inverse-cdf stage on its own, from identical (cdf, u): bit-exact indices and bins
+    i2, nb2 = ops.pdf_inverse(ref["cdf"].to(DEV), bins.to(DEV), u.to(DEV))
+    assert torch.equal(i2.cpu(), ref["inds"]) and torch.equal(nb2.cpu(), ref["new_bins"])
+    same = (inds.cpu() == ref["inds"]).float().mean()
+    assert same > 0.999, f"searchsorted agreement {same}"
+    assert_close(new_bins, ref["new_bins"], rtol=1e-4, what="new bins")
+    # merge: sortedness + permutation + consistency with the index (ties may order differently)
+    assert bool((merged[:, 1:] >= merged[:, :-1]).all())
+    assert torch.equal(torch.sort(index, -1)[0].cpu(), torch.arange(m + k).expand(n, -1))
+    cat = torch.cat([bins[:, :-1].to(DEV), new_bins[:, :-1]], -1)
+    assert torch.equal(torch.gather(cat, 1, index), merged[:, :-1])
+    assert torch.equal(ops.merge_rows(bins[:, :-1].to(DEV), new_bins[:, :-1].contiguous(), index), merged[:, :-1])
+
+
+# ---------------------------------------------------------------- ray generation (A1/A2)
+def test_raygen_golden():
+    ops = _ops()
+    g = load_golden("raygen")
+    n_cam = g["c2w"].shape[0]
+    intr = g.t("intr", DEV)[None].expand(n_cam, 4).contiguous()
+    for tag in ("shared", "percam", "off"):
+        dist = None if tag == "off" else g.t("dist", DEV)[None].expand(n_cam, 6).contiguous()
+        pa = None if tag == "off" else g.t(tag + "_pose", DEV).clone().requires_grad_(True)
+        o, d, up, area, dn = ops.RayGenFn.apply(g.t("coords", DEV), g.t("c2w", DEV), intr, dist, pa, 0.0)
+        for k, v in (("origins", o), ("directions", d), ("up_directions", up), ("pixel_area", area), ("directions_norm", dn)):
+            assert_close(v, g.t(f"{tag}_{k}"), rtol=2e-5 if k == "pixel_area" else 2e-6, what=f"{tag} {k}")
+        if pa is not None:
+            cot = g.t(tag + "_cot", DEV)
+            ((o * cot[0]).sum() + (d * cot[1]).sum() + (up * cot[2]).sum()).backward()
+            assert_close(pa.grad, g.t(tag + "_dpose"), rtol=2e-5, what=f"{tag} dpose")
+
+
+# ---------------------------------------------------------------- weights / compositing (A13/A14/A18/A19)
+def test_render_golden():
+    ops = _ops()
+    g = load_golden("render")
+    edges = g.t("edges", DEV)
+    starts, ends = edges[:, :-1].contiguous(), edges[:, 1:].contiguous()
+    dirs = g.t("dirs", DEV)
+    for tag, anneal in (("a1", 1.0), ("a03", 0.3)):
+        sdf, grad = g.t("sdf", DEV)[..., 0].requires_grad_(True), g.t("grad", DEV).requires_grad_(True)
+        s = torch.tensor([0.3], device=DEV, requires_grad=True)
+        inv_s = torch.exp(s * 10.0).clip(1e-6, 1e6)
+        w = ops.NeusWeightsFn.apply(sdf, grad, dirs, ends - starts, inv_s, None, anneal)
+        assert_close(w[..., None], g.t(tag + "_weights"), what="weights")
+        gs = torch.autograd.grad((w * g.t(tag + "_cot", DEV)[..., 0]).sum(), [sdf, grad, s])
+        assert_close(gs[0][..., None], g.t(tag + "_dsdf"), rtol=2e-5, what="dsdf")
+        assert_close(gs[1], g.t(tag + "_dgrad"), rtol=2e-5, what="dgrad")
+        assert_close(gs[2], g.t(tag + "_ds"), rtol=5e-5, what="ds")
+    w = g.t("a1_weights", DEV)[..., 0].requires_grad_(True)
+    vals, bg = g.t("comp_values", DEV).requires_grad_(True), g.t("comp_bg", DEV).requires_grad_(True)
+    col = ops.CompositeFn.apply(w, vals, bg)
+    assert_close(col, g.t("comp_color"), what="color")
+    gs = torch.autograd.grad((col * g.t("comp_cot", DEV)).sum(), [w, vals, bg])
+    assert_close(gs[0][..., None], g.t("comp_dw")); assert_close(gs[1], g.t("comp_dvalues")); assert_close(gs[2], g.t("comp_dbg"))
+    rn, rd, ra = ops.composite_aux(w, g.t("grad", DEV), starts, ends)
+    assert_close(rn, g.t("comp_normals")); assert_close(ra, g.t("comp_acc"))
+    assert_close(rd, g.t("comp_depth"), what="depth (unclipped == clipped here)")
+    dens = g.t("bg_density", DEV)[..., 0].requires_grad_(True)
+    bw = ops.DensityWeightsFn.apply(dens, ends - starts)
+    assert_close(bw[..., None], g.t("bg_weights"))
+    (bw * g.t("bg_cot", DEV)[..., 0]).sum().backward()
+    assert_close(dens.grad[..., None], g.t("bg_ddensity"), rtol=2e-5)
+    from multimodalstudio_b200.field_components import align_polarization_filters, stokes_to_intensity
+    st = g.t("pol_stokes", DEV)
+    st = torch.cat([torch.nn.functional.leaky_relu(st[:, :1]), st[:, 1:]], -1)
+    assert_close(stokes_to_intensity(align_polarization_filters(st, dirs, g.t("up", DEV))), g.t("pol_out"), rtol=2e-5)
+
+
+@pytest.mark.parametrize("n,s", [(1, 1), (3, 31), (257, 64), (100, 200), (33, 256)])
+def test_weights_vs_oracle_ragged(n, s):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(n + s)
+    sdf = torch.randn(n, s, generator=gen) * 0.1 + torch.linspace(0.4, -0.4, s)[None]
+    grad = torch.randn(n, s, 3, generator=gen)
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1)
+    deltas = torch.rand(n, s, generator=gen) * 0.05 + 0.01
+    mask = (torch.rand(n, generator=gen) > 0.3)
+    inv_s = torch.tensor([20.0])
+    cot = torch.randn(n, s, generator=gen)
+    ts = [t.clone().requires_grad_(True) for t in (sdf, grad, dirs, deltas, inv_s)]
+    w = O.neus_weights(ts[0][..., None], ts[1], ts[2][:, None], ts[3][..., None], ts[4], 0.7)[..., 0] * mask[:, None]
+    (w * cot).sum().backward()
+    tg = [t.to(DEV).requires_grad_(True) for t in (sdf, grad, dirs, deltas, inv_s)]
+    wg = ops.NeusWeightsFn.apply(tg[0], tg[1], tg[2], tg[3], tg[4], mask.to(DEV).to(torch.uint8), 0.7)
+    assert_close(wg, w, what="weights")
+    (wg * cot.to(DEV)).sum().backward()
+    for a, b, nm in zip(tg, ts, ("dsdf", "dgrad", "ddirs", "ddeltas", "dinv_s")):
+        assert_close(a.grad, b.grad, rtol=5e-5, atol=1e-7, what=nm)
+
+
+def test_sdf_taps_vs_oracle():
+    ops = _ops()
+    gen = torch.Generator().manual_seed(3)
+    n = 1000
+    delta = (2.0 / 1024) / np.sqrt(3)
+    sc = (torch.randn(n, 1, generator=gen) * 0.1).requires_grad_(True)
+    st = (sc.detach()[None] + torch.randn(4, n, 1, generator=gen) * 1e-3).requires_grad_(True)
+    g, h, nr = O.taps_gradients(sc, st, delta, True)
+    cots = [torch.randn(n, 3, generator=gen) for _ in range(3)]
+    ((g * cots[0]).sum() + (h * cots[1]).sum() * 1e-6 + (nr * cots[2]).sum()).backward()
+    scg, stg = sc.detach().to(DEV).requires_grad_(True), st.detach().to(DEV).requires_grad_(True)
+    gg, hg, ng = ops.SdfTapsFn.apply(scg[:, 0], stg[..., 0], float(delta), True)
+    assert torch.equal(gg.cpu(), g.detach()) and torch.equal(hg.cpu(), h.detach()), "IEEE-reproducible"
+    assert_close(ng, nr, rtol=2e-6)
+    ((gg * cots[0].to(DEV)).sum() + (hg * cots[1].to(DEV)).sum() * 1e-6 + (ng * cots[2].to(DEV)).sum()).backward()
+    assert_close(scg.grad, sc.grad, rtol=2e-5); assert_close(stg.grad, st.grad, rtol=2e-5)
+
+
+# ---------------------------------------------------------------- losses (A21/A22)
+def test_losses_golden():
+    from multimodalstudio_b200.model_components import (LossConfig, SkipSaturationLossConfig)
+    from multimodalstudio_b200.models import MOSAICK_PATTERNS, MODALITY_CHANNELS
+    ops = _ops()
+    g = load_golden("losses")
+    for mod in MODALITY_CHANNELS:
+        pat = torch.tensor(MOSAICK_PATTERNS[mod], dtype=torch.int32, device=DEV)
+        coords, rendered = g.t(mod + "_coords", DEV), g.t(mod + "_rendered", DEV).requires_grad_(True)
+        band, sel = ops.mosaick_bands(coords, pat.reshape(-1), pat.shape[0], pat.shape[1], rendered)
+        assert torch.equal(band.cpu(), O.mosaick_band(g.t(mod + "_coords"), MOSAICK_PATTERNS[mod])), "mosaick index bit-exact"
+        assert torch.equal(sel.cpu(), g.t(mod + "_selected")[:, 0])
+        cfg = SkipSaturationLossConfig(saturation_threshold=0.998) if mod == "polarization" else LossConfig()
+        loss, weight = cfg.setup(num_iterations=100)(rendered, g.t(mod + "_target", DEV), 10, pixel_coords=coords, mosaick_pattern=pat)
+        assert_close(loss, g.t(mod + "_loss"), what=mod + " loss")
+        loss.backward()
+        assert_close(rendered.grad, g.t(mod + "_drendered"), what=mod + " dloss")
+    gr, he = g.t("geo_gradients", DEV).requires_grad_(True), g.t("geo_hessians", DEV).requires_grad_(True)
+    eik, curv = ops.GeometryLossFn.apply(gr, he, None)
+    assert_close(eik, g.t("eikonal")); assert_close(curv, g.t("curvature"))
+    (eik + curv).backward()
+    assert_close(gr.grad, g.t("d_eikonal"), rtol=2e-5); assert_close(he.grad, g.t("d_curvature"), rtol=2e-5)
+
+
+def test_adamw_matches_torch():
+    ops = _ops()
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    p = torch.randn(100_003, device=DEV, generator=gen)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref], lr=1e-3, weight_decay=0.01, eps=1e-15)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        gr = torch.randn(p.shape, device=DEV, generator=gen)
+        ref.grad = gr.clone()
+        opt.step()
+        ops.adamw_step(p, gr, m, v, None, 1e-3, 0.9, 0.999, 1e-15, 0.01, step)
+    assert_close(p, ref, rtol=1e-6)
+    ss = torch.zeros(1, device=DEV)
+    ops.sumsq(p, ss)
+    assert_close(ss[0], (p.double() ** 2).sum(), rtol=1e-5)
