@@ -246,6 +246,12 @@ class NeuSSampler(Sampler):
             samples = uniform[mod]
             sbins = torch.cat([samples.spacing_starts[..., 0], samples.spacing_ends[..., -1:, 0]], dim=-1)
             nears, fars = rb.nears.detach(), rb.fars.detach()
+            if (rand.get("bins") or {}).get(mod) is not None:
+                # test hook: externally supplied final spacing bins [R, S+1] (isolates the sampler from the rest)
+                sbins = rand["bins"][mod]
+                eb = self.uniform_sampler.spacing_to_euclidean(sbins, nears, fars)
+                out[mod] = _samples_from_bins(rb, sbins, eb, rb.nears, rb.fars, self.uniform_sampler.spacing_to_euclidean)
+                continue
             new_samples, sdf = samples, None
             pdf_rand = (rand.get("pdf") or {}).get(mod)
             for it in range(self.config.num_upsample_steps):

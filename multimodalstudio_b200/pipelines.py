@@ -94,9 +94,10 @@ class FlatAdamW:
     def __init__(self, params: List[torch.nn.Parameter], lr=1e-3, weight_decay=0.01, eps=1e-15, betas=(0.9, 0.999),
                  max_norm: Optional[float] = 2.0):
         self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
+        align = 32      # floats: every parameter view starts on a 128-byte boundary (vector loads / atomics)
+        n = sum((p.numel() + align - 1) // align * align for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.empty(n, device=dev)
+        self.flat = torch.zeros(n, device=dev)
         self.grad = torch.zeros(n, device=dev)
         self.exp_avg = torch.zeros(n, device=dev)
         self.exp_avg_sq = torch.zeros(n, device=dev)
@@ -106,7 +107,7 @@ class FlatAdamW:
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p)
             p.grad = self.grad[off:off + k].view_as(p)
-            off += k
+            off += (k + align - 1) // align * align
         self.lr, self.wd, self.eps, self.betas, self.max_norm = lr, weight_decay, eps, betas, max_norm
         self.step_count = 0
         self.sumsq = torch.zeros(1, device=dev)
