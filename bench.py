@@ -126,6 +126,7 @@ def main():
     ap.add_argument("--all-heads", action="store_true", help="evaluate all M heads for every modality like the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.rays:
@@ -138,7 +139,8 @@ def main():
                            f"{wl['rays']} rays/GPU x {wl['n_c'] + wl['n_i']} samples (+{wl['bg']} background), hash grids 16x2^19x2 fp32, "
                            f"pose refinement SO3xR3 shared",
                "rays_per_gpu": wl["rays"], "samples_per_ray": wl["n_c"] + wl["n_i"], "parallelism": f"dp{world} (rays sharded, params replicated)",
-               "l2": "inputs >> L2 (2x64 MiB tables + >1 GiB of activations per step)", "peaks": peak_src}
+               "l2": "inputs >> L2 (2x64 MiB tables + >1 GiB of activations per step)", "peaks": peak_src,
+               "launch": "eager" if args.no_graph else "CUDA graphs (forward+backward | clip+AdamW)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -179,13 +181,18 @@ def main():
 
     def step_resident(i):
         cs, ts = resident[i % n_batches]
-        return pipe.train_step(BASE_STEP + i, cs, ts)
+        if args.no_graph:
+            return pipe.train_step(BASE_STEP + i, cs, ts)
+        return pipe.train_step_graphed(BASE_STEP + i, cs, ts)
 
     def step_e2e(i):
         cs, ts = pinned[i % n_batches]
-        csd = {m: c.to(dev, non_blocking=True) for m, c in cs.items()}
-        tsd = {m: t.to(dev, non_blocking=True) for m, t in ts.items()}
-        _, total = pipe.train_step(BASE_STEP + i, csd, tsd)
+        if args.no_graph:
+            csd = {m: c.to(dev, non_blocking=True) for m, c in cs.items()}
+            tsd = {m: t.to(dev, non_blocking=True) for m, t in ts.items()}
+            _, total = pipe.train_step(BASE_STEP + i, csd, tsd)
+        else:
+            _, total = pipe.train_step_graphed(BASE_STEP + i, cs, ts)     # pinned host -> static graph inputs inside
         return float(total.item())                      # device -> host read of the step's loss
 
     for i in range(args.warmup):
@@ -204,6 +211,8 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = _lib.launch_count() - l0
+    if not args.no_graph:
+        launches = pipe.graph_launches * args.steps      # every replay launches the kernels captured once
     clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([ms_total], device=dev)
     if world > 1:
@@ -233,16 +242,40 @@ def main():
     # instrumented entry points (same stream), outside the timed region so it is not perturbed
     roof, roof_hash = None, None
     if rank == 0:
-        _lib.start_kernel_timing({"mmsb_linear_fwd", "mmsb_linear_bwd_data", "mmsb_linear_bwd_weight", "mmsb_hashgrid_fwd", "mmsb_hashgrid_bwd"})
+        _lib.start_kernel_timing(None)
         for i in range(2):
-            step_resident(i)
+            cs, ts = resident[i % n_batches]
+            pipe.train_step(BASE_STEP + i, cs, ts)          # eager: events cannot be recorded inside a graph replay
         torch.cuda.synchronize()
         rec = _lib.stop_kernel_timing()
         flops = {"mmsb_linear_fwd": 0.0, "mmsb_linear_bwd_data": 0.0, "mmsb_linear_bwd_weight": 0.0}
         msk = {k: 0.0 for k in flops}
         cnt = {k: 0 for k in flops}
         hb = {"mmsb_hashgrid_fwd": [0.0, 0.0, 0], "mmsb_hashgrid_bwd": [0.0, 0.0, 0]}
+        tc_ms = 0.0
+        if os.environ.get("MMSB_BENCH_TABLE"):
+            # per entry point and layer shape: calls, total ms over the two instrumented steps (dev aid)
+            agg = {}
+            for name, ms, a in rec:
+                key = name
+                if name.startswith("mmsb_linear_fwd") or name.startswith("mmsb_linear_bwd_weight"):
+                    key = f"{name} n={a[6].value} k={a[7].value} o={a[8].value}"
+                elif name.startswith("mmsb_linear_bwd_data"):
+                    key = f"{name} n={a[9].value} k={a[10].value} o={a[11].value}"
+                c = agg.setdefault(key, [0, 0.0])
+                c[0] += 1
+                c[1] += ms
+            with open(os.environ["MMSB_BENCH_TABLE"], "w") as fh:
+                tot = sum(v[1] for v in agg.values())
+                fh.write(f"instrumented entry points: {tot / 2:.2f} ms per step\n")
+                for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                    fh.write(f"{v[1] / 2:9.3f} ms/step {v[0] // 2:5d} calls  {k}\n")
+        keep = {"mmsb_linear_fwd", "mmsb_linear_bwd_data", "mmsb_linear_bwd_weight", "mmsb_hashgrid_fwd", "mmsb_hashgrid_bwd"}
+        rec = [r for r in rec if (r[0][:-3] if r[0].endswith("_tc") else r[0]) in keep]
         for name, ms, a in rec:
+            if name.endswith("_tc"):
+                name = name[:-3]
+                tc_ms += ms
             if name == "mmsb_linear_fwd":
                 n, k, o = a[6].value, a[7].value, a[8].value
             elif name == "mmsb_linear_bwd_data":
@@ -261,7 +294,9 @@ def main():
         top = max(msk, key=lambda k: msk[k])
         if msk[top] > 0:
             ach = flops[top] / (msk[top] / 1e3) / 1e12
-            roof = {"kernel": top + " (fp32 SIMT GEMM path)", "bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s",
+            from multimodalstudio_b200 import ops as _ops
+            path = {0: "fp32 SIMT GEMM", 1: "tcgen05 TF32", 3: "tcgen05 3xTF32 (3 MMAs per product, fp32-accurate)"}[_ops.MLP_PRECISION]
+            roof = {"kernel": f"{top} ({path}; {100.0 * tc_ms / max(sum(msk.values()), 1e-9):.0f}% of layer time on tcgen05)", "bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s",
                     "frac": ach / tf_sust, "traffic": None, "launches": cnt[top] // 2, "ms_per_step": msk[top] / 2,
                     "peak_source": f"{peak_src} bf16 sustained (kernel timed inside a long step)"}
         hk = max(hb, key=lambda k: hb[k][1])

@@ -127,6 +127,31 @@ int mmsb_linear_bwd_data(const float* dz, int64_t lddz, const float* w, float* d
 int mmsb_linear_bwd_weight(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw,
                            float* db, int64_t n, int32_t in_dim, int32_t out_dim, mmsb_stream_t stream);
 
+/* A11 on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM; csrc/mlp_tc.cu).
+ * precision: 3 = "3xTF32" (hi/lo split, three TF32 MMAs per product: fp32-accurate, the parity mode),
+ *            1 = single-pass TF32 (the reference's GPU runs use fp16 autocast, mlp.py:152-171 under
+ *                torch.autocast; 1e-2 band).
+ * Weights are consumed pre-split and pre-swizzled ("packed"): pack once per optimiser step and layer, reuse
+ * for every evaluation of the step.  mmsb_linear_packed_size returns the number of floats of the packed
+ * operand for a logical [n_dim x k_dim] B matrix (forward: n_dim = out, k_dim = in; dgrad: n_dim = in,
+ * k_dim = out), or -1 on bad arguments. */
+int64_t mmsb_linear_packed_size(int32_t n_dim, int32_t k_dim, int32_t precision);
+/* w: effective [out_dim, in_dim] weight, row stride ldw.  transpose = 0 packs B = W (forward),
+ * transpose = 1 packs B = W^T (dgrad). */
+int mmsb_linear_pack_weight(const float* w, int64_t ldw, int32_t out_dim, int32_t in_dim, int32_t transpose,
+                            int32_t precision, float* packed, mmsb_stream_t stream);
+/* y = act(x W^T + b) with packed_w = pack(W, transpose = 0). */
+int mmsb_linear_fwd_tc(const float* x, int64_t ldx, const float* packed_w, const float* b, float* y, int64_t ldy,
+                       int64_t n, int32_t in_dim, int32_t out_dim, int32_t act, float act_param, int32_t precision,
+                       mmsb_stream_t stream);
+/* dx = dz W (* act_prev'(y_prev) when y_prev != NULL) with packed_wt = pack(W, transpose = 1). */
+int mmsb_linear_bwd_data_tc(const float* dz, int64_t lddz, const float* packed_wt, float* dx, int64_t lddx,
+                            const float* y_prev, int64_t ld_yprev, int32_t act_prev, float act_prev_param,
+                            int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision, mmsb_stream_t stream);
+/* dw[out,in] += dz^T x, db[out] += sum_n dz (db may be NULL); split over n, fp32 reductions in the L2. */
+int mmsb_linear_bwd_weight_tc(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw, float* db,
+                              int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision, mmsb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * A1/A2  ray generation.  ref: cameras/camera_optimizers.py:86-119, cameras/lie_groups.py:28-63,
  * model_components/ray_generators.py:54-81, cameras/cameras.py:460-703,
@@ -300,6 +325,12 @@ int mmsb_sdf_taps_bwd(const float* sdf_t, float four_delta, float delta_sq, cons
 int mmsb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                     const float* grad_scale, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int32_t step, int64_t n, mmsb_stream_t stream);
+/* The same update, replayable from a CUDA graph: the step-dependent scalars live in device memory,
+ * hyper = {lr, 1 - beta1^t, sqrt(1 - beta2^t)}; grad_sumsq (or NULL) + max_norm give the clip coefficient
+ * min(1, max_norm / (sqrt(sumsq) + 1e-6)) of clip_grad_norm_ (pipelines/base_pipeline.py:232-248). */
+int mmsb_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                        const float* grad_sumsq, float max_norm, const float* hyper, float beta1, float beta2,
+                        float eps, float weight_decay, int64_t n, mmsb_stream_t stream);
 /* sumsq[0] += sum grad^2 (for clip_grad_norm_, pipelines/base_pipeline.py:232-248). */
 int mmsb_sumsq(const float* x, float* sumsq, int64_t n, mmsb_stream_t stream);
 

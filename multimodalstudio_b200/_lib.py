@@ -150,9 +150,15 @@ _timed = None      # set of entry points to bracket with CUDA events (bench.py r
 _records = []
 
 
-def start_kernel_timing(names):
+class _Everything:
+    def __contains__(self, name):
+        return True
+
+
+def start_kernel_timing(names=None):
+    """names: entry points to bracket with CUDA events; None = every entry point."""
     global _timed, _records
-    _timed, _records = set(names), []
+    _timed, _records = (set(names) if names is not None else _Everything()), []
 
 
 def stop_kernel_timing():

@@ -171,6 +171,29 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 
+// Same update with the per-step scalars in device memory (hyper = {lr, 1 - beta1^t, sqrt(1 - beta2^t)}) and the
+// clip coefficient min(1, max_norm / (sqrt(sumsq) + 1e-6)) evaluated in the kernel: nothing step-dependent is a
+// launch argument, so the launch can be replayed from a CUDA graph.
+__global__ void __launch_bounds__(256) adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v,
+                                                        const float* __restrict__ grad_sumsq, float max_norm,
+                                                        const float* __restrict__ hyper, float beta1, float beta2,
+                                                        float eps, float wd, int64_t n) {
+  const float lr = __ldg(hyper), bc1 = __ldg(hyper + 1), bc2_sqrt = __ldg(hyper + 2);
+  float gs = 1.f;
+  if (grad_sumsq) gs = fminf(__fdiv_rn(max_norm, __fadd_rn(__fsqrt_rn(__ldg(grad_sumsq)), 1e-6f)), 1.f);
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float gr = g[i] * gs;
+    float pv = p[i];
+    pv *= (1.f - lr * wd);
+    const float mi = beta1 * m[i] + (1.f - beta1) * gr;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gr * gr;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pv - (lr / bc1) * (mi / denom);
+  }
+}
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
   float acc = 0.f;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
@@ -254,6 +277,19 @@ extern "C" int mmsb_adamw_step(float* param, const float* grad, float* exp_avg, 
   adamw_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, grad_scale, lr, beta1,
                                                                 beta2, eps, weight_decay, float(bc1), float(sqrt(bc2)), n);
   return check_launch("adamw_step");
+}
+
+extern "C" int mmsb_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                   const float* grad_sumsq, float max_norm, const float* hyper, float beta1, float beta2,
+                                   float eps, float weight_decay, int64_t n, mmsb_stream_t stream) {
+  MMSB_REQUIRE(n >= 0, "adamw_step_dev: bad arguments");
+  if (n == 0) return MMSB_OK;
+  MMSB_REQUIRE(param && grad && exp_avg && exp_avg_sq && hyper, "adamw_step_dev: NULL pointer");
+  int64_t blocks = ceil_div(n, 256);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  adamw_dev_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, grad_sumsq, max_norm,
+                                                                    hyper, beta1, beta2, eps, weight_decay, n);
+  return check_launch("adamw_step_dev");
 }
 
 extern "C" int mmsb_sumsq(const float* x, float* sumsq, int64_t n, mmsb_stream_t stream) {

@@ -1,5 +1,5 @@
 // A11 — dense layers of the field MLPs, fp32 SIMT path (parity mode: plain IEEE fp32 accumulation).
-// ref: src/field_components/mlp.py:152-171.  The tcgen05 path lives in mlp_tc.cu.
+// ref: src/field_components/mlp.py:152-171.  The tcgen05 path (mmsb_linear_*_tc) lives in mlp_tc.cu.
 //
 // One register-tiled SGEMM (128x128x16 tiles, 8x8 per thread, double-buffered shared memory, LDS.128
 // fragments) serves the three products of a layer:
@@ -9,7 +9,6 @@
 // Layers with out_dim <= 16 (sdf-only last layer, modality heads, density head) use skinny
 // row-streaming kernels instead of padding a 128-wide tile.
 #include "common.cuh"
-#include <stdlib.h>
 
 namespace mmsb {
 
@@ -268,30 +267,9 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
 
 }  // namespace mmsb
 
-namespace mmsb {
-// tcgen05 path (mlp_tc.cu)
-int tc_linear_fwd(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int64_t n,
-                  int in_dim, int out_dim, int act, float act_param, cudaStream_t s);
-int tc_linear_bwd_data(const float* dz, int64_t lddz, const float* w, float* dx, int64_t lddx, const float* y_prev,
-                       int64_t ld_yprev, int act_prev, float act_prev_param, int64_t n, int in_dim, int out_dim,
-                       cudaStream_t s);
-int tc_linear_bwd_weight(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw, int64_t n, int in_dim,
-                         int out_dim, cudaStream_t s);
-}  // namespace mmsb
-
 using namespace mmsb;
 
 static bool valid_act(int a) { return a >= MMSB_ACT_NONE && a <= MMSB_ACT_SIGMOID; }
-
-// MMSB_MLP_PATH=simt keeps every layer on the fp32 SIMT GEMM; default: tcgen05 3xTF32 for wide layers.
-static bool use_tensor_cores() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MMSB_MLP_PATH");
-    v = (e && e[0] == 's') ? 0 : 1;
-  }
-  return v == 1;
-}
 
 extern "C" int mmsb_linear_fwd(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy,
                                int64_t n, int32_t in_dim, int32_t out_dim, int32_t act, float act_param,
@@ -308,7 +286,6 @@ extern "C" int mmsb_linear_fwd(const float* x, int64_t ldx, const float* w, cons
                                                                       act_param);
     return check_launch("linear_fwd(skinny)");
   }
-  if (use_tensor_cores() && n >= 128) return tc_linear_fwd(x, ldx, w, b, y, ldy, n, in_dim, out_dim, act, act_param, s);
   GemmArgs g{};
   g.A = x; g.lda = ldx; g.B = w; g.ldb = in_dim; g.C = y; g.ldc = ldy;
   g.M = n; g.N = out_dim; g.K = in_dim; g.bias = b; g.act = act; g.act_param = act_param;
@@ -344,8 +321,6 @@ extern "C" int mmsb_linear_bwd_data(const float* dz, int64_t lddz, const float* 
                                                                             act_prev, act_prev_param, n, in_dim, out_dim);
     return check_launch("linear_bwd_data(skinny)");
   }
-  if (use_tensor_cores() && n >= 128)
-    return tc_linear_bwd_data(dz, lddz, w, dx, lddx, y_prev, ld_yprev, act_prev, act_prev_param, n, in_dim, out_dim, s);
   GemmArgs g{};
   g.A = dz; g.lda = lddz; g.B = w; g.ldb = in_dim; g.C = dx; g.ldc = lddx;
   g.M = n; g.N = in_dim; g.K = out_dim;
@@ -377,7 +352,6 @@ extern "C" int mmsb_linear_bwd_weight(const float* dz, int64_t lddz, const float
                                                                              rows_per_block);
     return check_launch("linear_bwd_weight(skinny)");
   }
-  if (use_tensor_cores() && n >= 512) return tc_linear_bwd_weight(dz, lddz, x, ldx, dw, n, in_dim, out_dim, s);
   GemmArgs g{};
   g.A = dz; g.lda = lddz; g.B = x; g.ldb = ldx; g.C = dw; g.ldc = in_dim;
   g.M = out_dim; g.N = in_dim; g.K = n;

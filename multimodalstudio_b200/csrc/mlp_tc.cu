@@ -1,66 +1,58 @@
-// A11 — dense layers on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+// A11 — dense layers of the field MLPs on the 5th-generation tensor cores (tcgen05.mma, accumulators in
+// TMEM).  ref: src/field_components/mlp.py:152-171 (y = act(W x + b) per layer).
 //
-// One kernel, three products (forward, dgrad, wgrad) of a layer, fp32 in / fp32 out, fp32-accurate:
-// every fp32 operand x is split in shared memory into hi = tf32(x) and lo = x - hi and the product is
-// accumulated as hi*hi + lo*hi + hi*lo (3 x kind::tf32, fp32 accumulation in TMEM), which keeps the
-// 1e-5 parity band of the fp32 reference while running on the tensor pipe.
+// fp32 in / fp32 out.  Precision 3 ("3xTF32"): every fp32 operand x is split into hi = tf32(x) and
+// lo = tf32(x - hi) and the product is accumulated as lo*hi + hi*lo + hi*hi (three kind::tf32 MMAs, fp32
+// accumulation in TMEM), which keeps the 1e-5 parity band of the fp32 reference on the tensor pipe.
+// Precision 1: single-pass TF32 (the reference's GPU runs use fp16 autocast; 1e-2 band).
 //
-// Tile: D[128 x BN] (BN <= 256) per CTA, K in blocks of 32 fp32 (one 128-byte swizzle row), two shared-memory
-// stages.  All 8 warps stage operands (global -> registers -> hi/lo split -> K-major SWIZZLE_128B shared
-// memory; transposing on the fly where the global layout is MN-major), one elected thread issues the MMAs,
-// tcgen05.commit signals stage reuse / accumulator completion through mbarriers, all 8 warps drain TMEM with
-// tcgen05.ld (32 lanes x 32 columns per instruction) and apply the fused epilogue (bias + activation,
-// activation derivative of the previous layer, or split-K atomics for the weight gradient).
+// Two persistent, warp-specialised kernels, one CTA per SM:
+//   tc_rows_kernel  (forward, dgrad)   D[rows x N] = A[rows x K] * Bp[N x K]^T
+//       A  = activations, fp32 in global memory; 8 producer warps load them with a register prefetch, split
+//            them into hi/lo and store them into K-major SWIZZLE_128B shared-memory tiles;
+//       Bp = weights pre-split and pre-swizzled by pack_weight_kernel (once per step and layer), so one
+//            bulk async copy (TMA, cp.async.bulk + mbarrier complete_tx) lands a k-block of B in its stage;
+//       1 thread issues tcgen05.mma into one of two 128x256 fp32 accumulators in TMEM (512 columns), so the
+//       4 epilogue warps (tcgen05.ld -> bias/activation or activation derivative -> shared-memory transpose
+//       -> coalesced 128-byte stores) drain tile i while the MMAs of tile i+1 run.
+//   tc_wgrad_kernel (weight gradient)  dW[out x in] += dz[rows x out]^T * x[rows x in], split over rows
+//       both operands are MN-major in global memory and are staged without a transpose into MN-major
+//       SWIZZLE_128B_BASE32B tiles; the bias gradient (column sums of dz) is accumulated by the producers on the way;
+//       partial tiles are combined with coalesced fp32 reductions (red.global.add).
 #include "common.cuh"
 
 namespace mmsb {
+namespace tc {
 
-// activation helpers (same definitions as mlp_simt.cu)
-__device__ __forceinline__ float tc_act_fwd(float z, int act, float p) {
-  switch (act) {
-    case MMSB_ACT_RELU: return fmaxf(z, 0.f);
-    case MMSB_ACT_SOFTPLUS: { const float zb = z * p; return zb > 20.f ? z : log1pf(expf(zb)) / p; }
-    case MMSB_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
-    default: return z;
-  }
+constexpr int TM = 128;            // rows of one accumulator (UMMA M)
+constexpr int TK = 32;             // fp32 per k-block = one 128-byte swizzle row
+constexpr int NT = 256;            // widest accumulator (UMMA N)
+constexpr int PART = TM * 128;     // bytes of one A part (hi or lo) of a stage
+constexpr int BPART = NT * 128;    // bytes reserved for one B part of a stage
+constexpr int EPI_WARPS = 8, PROD_WARPS = 8;                 // two epilogue warps per TMEM lane quadrant
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int THREADS = (EPI_WARPS + PROD_WARPS + 2) * 32;   // + B-loader warp + MMA warp
+constexpr int CH = 16;                                       // accumulator columns per epilogue chunk
+constexpr int STG_LD = 20;                                   // floats per row of the epilogue transpose buffer
+constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
+constexpr int MAX_STAGES = 4;
+
+__host__ __device__ constexpr int stage_bytes(int nparts) { return nparts * (PART + BPART); }
+__host__ __device__ constexpr int num_stages(int nparts) { return nparts == 2 ? 2 : 4; }
+__host__ __device__ constexpr int smem_bytes(int nparts) {
+  return num_stages(nparts) * stage_bytes(nparts) + STG_BYTES + 256 /*barriers*/ + 1024 /*alignment*/;
 }
-__device__ __forceinline__ float tc_act_bwd_from_y(float y, int act, float p) {
-  switch (act) {
-    case MMSB_ACT_RELU: return y > 0.f ? 1.f : 0.f;
-    case MMSB_ACT_SOFTPLUS: { const float yb = y * p; return yb > 20.f ? 1.f : -expm1f(-yb); }
-    case MMSB_ACT_SIGMOID: return y * (1.f - y);
-    default: return 1.f;
-  }
-}
 
-struct TcArgs {
-  const float* A; int64_t lda;   // A_KC: A(m,k) = A[m*lda + k]; else A(m,k) = A[k*lda + m]
-  const float* B; int64_t ldb;   // B_KC: B(n,k) = B[n*ldb + k]; else B(n,k) = B[k*ldb + n]
-  float* C; int64_t ldc;
-  int64_t M; int64_t N; int64_t K;
-  const float* bias; int act; float act_param;
-  const float* yprev; int64_t ld_yprev; int act_prev; float act_prev_param;
-  int64_t k_per_split;
-  int bn;                        // N tile (multiple of 16, <= 256)
-};
-
-constexpr int TM = 128, TK = 32, TC_THREADS = 256, TC_STAGES = 2;
-constexpr int A_TILE_BYTES = TM * 128;           // 128 rows x 128 B (one operand, hi or lo)
-constexpr int B_TILE_BYTES = 256 * 128;          // up to 256 rows
-
-__host__ __device__ constexpr int tc_stage_bytes() { return 2 * A_TILE_BYTES + 2 * B_TILE_BYTES; }
-constexpr int TC_SMEM_BYTES = TC_STAGES * tc_stage_bytes() + 1024 /*align*/ + 64 /*barriers*/;
-
-enum { TC_EPI_FWD = 0, TC_EPI_DGRAD = 1, TC_EPI_ATOMIC = 2 };
-
+// ---- PTX wrappers -----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -70,8 +62,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-  } while (!done);
+    if (!done && spins > (1u << 24)) {
+      printf("mms_b200 tcgen05: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+             bar, parity);
+      __trap();
+    }
+  }
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -81,252 +92,688 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100: version 1): 8-row atoms of 1024 B.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+// Shared-memory matrix descriptor (sm_100: version 1), SWIZZLE_128B.
+//  K-major : rows of 128 B (32 fp32 along K), 8-row atoms of 1024 B; SBO = 1024, LBO unused.
+//  MN-major (32-bit operands only come as SWIZZLE_128B_BASE32B): rows of 128 B (32 fp32 along M/N) per k, whose
+//            32-byte chunks are XOR-swizzled with k % 4; 4-k atoms of 512 B (SBO), 32-wide panels LBO apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
   uint64_t d = 0;
-  d |= uint64_t((saddr & 0x3FFFF) >> 4);        // start address
-  d |= uint64_t(1) << 16;                       // leading byte offset (unused for swizzled K-major)
-  d |= uint64_t(1024 >> 4) << 32;               // stride byte offset between 8-row groups
-  d |= uint64_t(1) << 46;                       // descriptor version (Blackwell)
-  d |= uint64_t(2) << 61;                       // SWIZZLE_128B
+  d |= uint64_t((saddr & 0x3FFFF) >> 4);
+  d |= uint64_t(lbo_bytes >> 4) << 16;
+  d |= uint64_t(sbo_bytes >> 4) << 32;
+  d |= uint64_t(1) << 46;   // descriptor version (Blackwell)
+  d |= uint64_t(layout) << 61;   // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
-__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
-  // c_format F32 (1 << 4), a/b format TF32 (2 << 7, 2 << 10), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
-  return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(TM >> 4) << 24);
+// c_format F32 (1 << 4), a/b format TF32 (2 << 7, 2 << 10), a/b major at bits 15/16 (1 = MN-major),
+// N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n, bool mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (mn_major ? (3u << 15) : 0u) | (uint32_t(n >> 3) << 17) |
+         (uint32_t(TM >> 4) << 24);
 }
-
-// byte offset of element (row r, k) inside a [rows x 32 fp32] K-major SWIZZLE_128B tile
-__device__ __forceinline__ uint32_t sw128(int r, int k) {
-  return uint32_t(r) * 128u + ((uint32_t(k >> 2) ^ uint32_t(r & 7)) << 4) + uint32_t(k & 3) * 4u;
-}
-// hi = x rounded to nearest tf32 (unbiased, unlike the hardware's truncation), lo = tf32(x - hi)
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-__device__ __forceinline__ void split_store(uint8_t* hi, uint8_t* lo, uint32_t off, float v) {
-  const float h = tf32_rna(v);
-  *reinterpret_cast<float*>(hi + off) = h;
-  *reinterpret_cast<float*>(lo + off) = tf32_rna(v - h);
+// byte offset of 16-byte chunk c (4 fp32 along M/N) of k-row k in an MN-major SWIZZLE_128B_BASE32B tile whose 32-wide
+// panels hold TK k-rows each
+__device__ __forceinline__ uint32_t mn_offset(int c, int k) {
+  return uint32_t(c >> 3) * uint32_t(TK * 128) + uint32_t(k) * 128u + (uint32_t(((c & 7) >> 1) ^ (k & 3)) << 5) +
+         (uint32_t(c & 1) << 4);
+}
+template <int NPARTS>
+__device__ __forceinline__ void split_store4(uint8_t* hi, uint8_t* lo, uint32_t off, const float4& v) {
+  float4 h;
+  h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+  *reinterpret_cast<float4*>(hi + off) = h;
+  if (NPARTS == 2) {
+    float4 l;
+    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+    *reinterpret_cast<float4*>(lo + off) = l;
+  }
+}
+// 16 bytes at (row r, k..k+3) of P[r*ld + k]; zero outside [0,rmax) x [0,kmax)
+__device__ __forceinline__ float4 load4(const float* __restrict__ p, int64_t ld, int64_t r, int64_t rmax, int64_t k,
+                                        int64_t kmax, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < rmax && k < kmax) {
+    const float* src = p + r * ld + k;
+    if (vec && k + 3 < kmax) {
+      v = __ldg(reinterpret_cast<const float4*>(src));
+    } else {
+      v.x = __ldg(src);
+      if (k + 1 < kmax) v.y = __ldg(src + 1);
+      if (k + 2 < kmax) v.z = __ldg(src + 2);
+      if (k + 3 < kmax) v.w = __ldg(src + 3);
+    }
+  }
+  return v;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Stages one operand k-block: rows [r0, r0+nrows) x k [k0, k0+32) -> hi/lo tiles.
-template <bool KC>
-__device__ __forceinline__ void stage_operand(const float* __restrict__ p, int64_t ld, int64_t r0, int64_t rmax, int nrows,
-                                              int64_t k0, int64_t kmax, uint8_t* hi, uint8_t* lo) {
-  const int t = threadIdx.x;
-  if (KC) {
-    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((k0 & 3) == 0);
-    // thread -> (row = t/8 + 32*i, 16-byte chunk = t%8)
-    const int c = t & 7;
-    for (int r = t >> 3; r < nrows; r += 32) {
-      const int64_t gr = r0 + r, gk = k0 + c * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gr < rmax) {
-        const float* src = p + gr * ld + gk;
-        if (vec && gk + 3 < kmax) {
-          v = __ldg(reinterpret_cast<const float4*>(src));
-        } else {
-          if (gk < kmax) v.x = __ldg(src);
-          if (gk + 1 < kmax) v.y = __ldg(src + 1);
-          if (gk + 2 < kmax) v.z = __ldg(src + 2);
-          if (gk + 3 < kmax) v.w = __ldg(src + 3);
-        }
-      }
-      const uint32_t off = uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4);
-      float4 h, l;
-      h.x = tf32_rna(v.x); l.x = tf32_rna(v.x - h.x);
-      h.y = tf32_rna(v.y); l.y = tf32_rna(v.y - h.y);
-      h.z = tf32_rna(v.z); l.z = tf32_rna(v.z - h.z);
-      h.w = tf32_rna(v.w); l.w = tf32_rna(v.w - h.w);
-      *reinterpret_cast<float4*>(hi + off) = h;
-      *reinterpret_cast<float4*>(lo + off) = l;
+// The epilogues evaluate Softplus through the MUFU units (ex2 / lg2 approximations, ~2^-22 relative): their error is
+// far below the 3xTF32 product error, and the IEEE expf / log1pf sequences would cost more issue slots per tile than
+// the whole MMA mainloop leaves free.
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float act_fwd(float z, int act, float p) {
+  switch (act) {
+    case MMSB_ACT_RELU: return fmaxf(z, 0.f);
+    case MMSB_ACT_SOFTPLUS: {
+      // max(z, 0) + log1p(exp(-|beta z|)) / beta; equals z exactly for beta z > 20 like torch's threshold
+      const float e = fast_ex2(-fabsf(z * p) * 1.4426950408889634f);
+      return fmaxf(z, 0.f) + fast_lg2(1.f + e) * (0.6931471805599453f / p);
     }
-  } else {
-    // MN-contiguous in global memory: lanes run along the rows (coalesced), warps along k; transposed store
-    const int lane = t & 31, w = t >> 5;
-    for (int k = w; k < TK; k += 8) {
-      const int64_t gk = k0 + k;
-      for (int r = lane; r < nrows; r += 32) {
-        const int64_t gr = r0 + r;
-        float v = 0.f;
-        if (gr < rmax && gk < kmax) v = __ldg(p + gk * ld + gr);
-        split_store(hi, lo, sw128(r, k), v);
-      }
+    case MMSB_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
+    default: return z;
+  }
+}
+__device__ __forceinline__ float act_bwd_from_y(float y, int act, float p) {
+  switch (act) {
+    case MMSB_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case MMSB_ACT_SOFTPLUS: return 1.f - fast_ex2(-y * p * 1.4426950408889634f);      // sigmoid(beta z) = 1 - exp(-beta y)
+    case MMSB_ACT_SIGMOID: return y * (1.f - y);
+    default: return 1.f;
+  }
+}
+
+// ---- packed weights ---------------------------------------------------------------------------------------
+// Operand B of a rows product: logical [N x K], element (n, k) = w[n*ldw + k] (forward: B = W) or
+// w[k*ldw + n] (dgrad: B = W^T).  Packed as n-tiles of up to 256 rows (N padded to a multiple of 16), each a
+// sequence of k-blocks of 32 (K padded), each k-block = [hi tile][lo tile], a tile = rows x 128 B, SWIZZLE_128B.
+__host__ __device__ inline int pad16(int n) { return (n + 15) / 16 * 16; }
+__host__ __device__ inline int tile_width(int n_pad, int nt) { return n_pad - nt * NT < NT ? n_pad - nt * NT : NT; }
+__host__ __device__ inline int64_t packed_floats(int n, int k, int nparts) {
+  return int64_t(pad16(n)) * TK * ((k + TK - 1) / TK) * nparts;
+}
+
+__global__ void pack_weight_kernel(const float* __restrict__ w, int64_t ldw, int n, int k, int transpose, int nparts,
+                                   float* __restrict__ packed) {
+  const int n_pad = pad16(n), nkb = (k + TK - 1) / TK;
+  const int64_t total = int64_t(n_pad) * nkb * TK;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int kk = int(i % (nkb * TK)), nn = int(i / (nkb * TK));
+    float v = 0.f;
+    if (nn < n && kk < k) v = transpose ? __ldg(w + int64_t(kk) * ldw + nn) : __ldg(w + int64_t(nn) * ldw + kk);
+    const int nt = nn / NT, r = nn % NT, wdt = tile_width(n_pad, nt);
+    const int kb = kk / TK, kin = kk % TK;
+    const int64_t base = int64_t(nt) * NT * TK * nkb * nparts + int64_t(kb) * nparts * wdt * TK;
+    const int64_t off = int64_t(r) * TK + (((kin >> 2) ^ (r & 7)) << 2) + (kin & 3);
+    const float h = tf32_rna(v);
+    packed[base + off] = h;
+    if (nparts == 2) packed[base + int64_t(wdt) * TK + off] = tf32_rna(v - h);
+  }
+}
+
+// ---- epilogue of one 32-row x 32-column chunk: registers -> transpose buffer -> coalesced global ------------
+enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_ATOMIC = 2 };
+
+struct EpiArgs {
+  float* C; int64_t ldc; int64_t M; int N;   // logical extents of C
+  const float* bias; int act; float act_param;
+  const float* yprev; int64_t ld_yprev; int act_prev; float act_prev_param;
+};
+
+template <int ACT>
+__device__ __forceinline__ float4 act_fwd4(float4 x, float p) {
+  x.x = act_fwd(x.x, ACT, p); x.y = act_fwd(x.y, ACT, p); x.z = act_fwd(x.z, ACT, p); x.w = act_fwd(x.w, ACT, p);
+  return x;
+}
+template <int ACT>
+__device__ __forceinline__ float4 act_bwd4(float4 y, float p) {
+  y.x = act_bwd_from_y(y.x, ACT, p); y.y = act_bwd_from_y(y.y, ACT, p); y.z = act_bwd_from_y(y.z, ACT, p);
+  y.w = act_bwd_from_y(y.w, ACT, p);
+  return y;
+}
+
+// A chunk is 32 rows x CH columns of the accumulator.  After the transpose through shared memory lane l owns the 4
+// consecutive columns col0 + 4 (l % 4) of the rows l / 4 + 8 i (i < 4): bias / activation / derivative work is per
+// float4 and a warp's global accesses cover 64 contiguous bytes of 8 rows.
+struct YPrev {
+  float4 v[4];
+};
+
+template <int EPI>
+__device__ __forceinline__ void load_yprev(const EpiArgs& e, YPrev& y, int lane, int64_t row0, int col0, bool vec_y) {
+  if (EPI != EPI_DGRAD || e.yprev == nullptr || e.act_prev == MMSB_ACT_NONE) return;
+  const int col = col0 + 4 * (lane & 3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t row = row0 + (lane >> 2) + 8 * i;
+    y.v[i] = load4(e.yprev, e.ld_yprev, row, e.M, col, e.N, vec_y);
+  }
+}
+
+template <int EPI, int ACT>
+__device__ __forceinline__ void epilogue_rows(const EpiArgs& e, const float* stg, const YPrev& yp, int lane, int64_t row0,
+                                              int col0, bool vec_ok) {
+  const int q4 = lane & 3;
+  const int col = col0 + 4 * q4;
+  if (col >= e.N) return;
+  const bool full = col + 3 < e.N;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (EPI == EPI_FWD && e.bias) {
+    b4.x = __ldg(e.bias + col);
+    if (col + 1 < e.N) b4.y = __ldg(e.bias + col + 1);
+    if (col + 2 < e.N) b4.z = __ldg(e.bias + col + 2);
+    if (col + 3 < e.N) b4.w = __ldg(e.bias + col + 3);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i;
+    const int64_t row = row0 + r;
+    if (row >= e.M) continue;
+    float4 x = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * q4);
+    float* dst = e.C + row * e.ldc + col;
+    if (EPI == EPI_FWD) {
+      x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+      x = act_fwd4<ACT>(x, e.act_param);
+    } else if (EPI == EPI_DGRAD && ACT != MMSB_ACT_NONE) {
+      const float4 y = act_bwd4<ACT>(yp.v[i], e.act_prev_param);
+      x.x *= y.x; x.y *= y.y; x.z *= y.z; x.w *= y.w;
+    }
+    if (EPI == EPI_ATOMIC) {
+      atomicAdd(dst, x.x);
+      if (col + 1 < e.N) atomicAdd(dst + 1, x.y);
+      if (col + 2 < e.N) atomicAdd(dst + 2, x.z);
+      if (col + 3 < e.N) atomicAdd(dst + 3, x.w);
+    } else if (vec_ok && full) {
+      *reinterpret_cast<float4*>(dst) = x;
+    } else {
+      dst[0] = x.x;
+      if (col + 1 < e.N) dst[1] = x.y;
+      if (col + 2 < e.N) dst[2] = x.z;
+      if (col + 3 < e.N) dst[3] = x.w;
     }
   }
 }
 
-template <bool A_KC, bool B_KC, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(TcArgs g) {
+// One chunk: lane owns row (row0 + lane) in registers -> transpose buffer -> epilogue_rows.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, uint32_t (&v)[CH], float* stg, const YPrev& yp, int lane,
+                                               int64_t row0, int col0, bool vec_ok) {
+#pragma unroll
+  for (int j = 0; j < CH / 4; ++j)
+    *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) =
+        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                    __uint_as_float(v[4 * j + 3]));
+  __syncwarp();
+  const int act = EPI == EPI_FWD ? e.act : (EPI == EPI_DGRAD && e.yprev ? e.act_prev : MMSB_ACT_NONE);
+  switch (act) {
+    case MMSB_ACT_RELU: epilogue_rows<EPI, MMSB_ACT_RELU>(e, stg, yp, lane, row0, col0, vec_ok); break;
+    case MMSB_ACT_SOFTPLUS: epilogue_rows<EPI, MMSB_ACT_SOFTPLUS>(e, stg, yp, lane, row0, col0, vec_ok); break;
+    case MMSB_ACT_SIGMOID: epilogue_rows<EPI, MMSB_ACT_SIGMOID>(e, stg, yp, lane, row0, col0, vec_ok); break;
+    default: epilogue_rows<EPI, MMSB_ACT_NONE>(e, stg, yp, lane, row0, col0, vec_ok); break;
+  }
+  __syncwarp();
+}
+
+// All chunks of one accumulator that belong to this warp (quadrant q = warp % 4, chunks c = warp / 4, +2, ...).
+// `release` is called by every lane right after the warp's last TMEM read (frees the accumulator for the MMA warp).
+template <int EPI, typename Release>
+__device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_acc, int w, float* stg, int warp, int lane,
+                                              int64_t row_base, int col_base, bool vec_ok, bool vec_y, YPrev& y_cur,
+                                              Release release) {
+  const int q = warp & 3, first = warp >> 2;
+  const int nch = (w + CH - 1) / CH;
+  const int64_t row0 = row_base + q * 32;
+  if (first >= nch) {
+    release();
+    return;
+  }
+  for (int c = first; c < nch; c += 2) {
+    uint32_t v[CH];
+    tmem_ld16(tmem_acc + uint32_t(c * CH) + (uint32_t(q * 32) << 16), v);
+    if (c + 2 >= nch) release();
+    YPrev y_next;
+    if (c + 2 < nch) load_yprev<EPI>(e, y_next, lane, row0, col_base + (c + 2) * CH, vec_y);
+    epilogue_chunk<EPI>(e, v, stg, y_cur, lane, row0, col_base + c * CH, vec_ok);
+    if (c + 2 < nch) y_cur = y_next;
+  }
+}
+
+// ---- forward / dgrad ----------------------------------------------------------------------------------------
+struct RowsArgs {
+  const float* A; int64_t lda; int64_t M; int K;
+  const float* Bp; int N;
+  EpiArgs epi;
+  int n_tiles; int nkb; int64_t total_tiles;
+};
+
+template <int NPARTS, int EPI>
+__global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g) {
+  constexpr int S = num_stages(NPARTS);
+  constexpr int STAGE = stage_bytes(NPARTS);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * tc_stage_bytes());   // [0..1] stage free, [2] accumulator done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* stg_all = reinterpret_cast<float*>(smem + S * STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * STAGE + STG_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * MAX_STAGES), bar_tempty = smem_u32(bars + 2 * MAX_STAGES + 2);
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int bn = g.bn;
-  const int64_t m0 = int64_t(blockIdx.x) * TM, n0 = int64_t(blockIdx.y) * bn;
-  const int64_t kbeg = int64_t(blockIdx.z) * g.k_per_split;
-  const int64_t kend = min(g.K, kbeg + g.k_per_split);
-  if (kbeg >= kend) return;
-  const int nkb = int((kend - kbeg + TK - 1) / TK);
-  const int64_t nb_left = ((g.N - n0 + 15) / 16) * 16;
-  const int nrows_b = int(nb_left < int64_t(bn) ? nb_left : int64_t(bn));   // rows of B actually staged (rest of the tile unused)
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < uint32_t(bn)) tmem_cols <<= 1;
-
   if (t == 0) {
-    mbar_init(smem_u32(&bars[0]), 1);
-    mbar_init(smem_u32(&bars[1]), 1);
-    mbar_init(smem_u32(&bars[2]), 1);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8 * s, PROD_THREADS + 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, EPI_WARPS * 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = *tmem_slot;
-  const uint32_t idesc = make_idesc_tf32(nrows_b);
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_pad = pad16(g.N);
+  const int last_ksteps = (g.K - (g.nkb - 1) * TK + 7) / 8;
 
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb & 1;
-    uint8_t* st = smem + s * tc_stage_bytes();
-    uint8_t *a_hi = st, *a_lo = st + A_TILE_BYTES, *b_hi = st + 2 * A_TILE_BYTES, *b_lo = st + 2 * A_TILE_BYTES + B_TILE_BYTES;
-    if (kb >= 2) mbar_wait(smem_u32(&bars[s]), uint32_t(((kb >> 1) - 1) & 1));   // MMAs that read this stage are done
-    const int64_t k0 = kbeg + int64_t(kb) * TK;
-    stage_operand<A_KC>(g.A, g.lda, m0, g.M, TM, k0, kend, a_hi, a_lo);
-    stage_operand<B_KC>(g.B, g.ldb, n0, g.N, nrows_b, k0, kend, b_hi, b_lo);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-    __syncthreads();
-    if (t == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint64_t dah = make_desc(smem_u32(a_hi)), dal = make_desc(smem_u32(a_lo));
-      const uint64_t dbh = make_desc(smem_u32(b_hi)), dbl = make_desc(smem_u32(b_lo));
-#pragma unroll
-      for (int j = 0; j < TK / 8; ++j) {
-        const uint64_t adv = uint64_t((j * 32) >> 4);     // 8 tf32 = 32 bytes along K inside the swizzle row
-        umma_tf32(tmem_d, dal + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
-        umma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
-        umma_tf32(tmem_d, dah + adv, dbh + adv, idesc, 1u);
-      }
-      umma_commit(smem_u32(&bars[s]));
-      if (kb == nkb - 1) umma_commit(smem_u32(&bars[2]));
+  if (warp < EPI_WARPS) {
+    // ================= epilogue: TMEM -> registers -> global =================
+    float* stg = stg_all + warp * 32 * STG_LD;
+    const bool vec_ok = ((g.epi.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.epi.C) & 15) == 0);
+    const bool vec_y = ((g.epi.ld_yprev & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.epi.yprev) & 15) == 0);
+    uint32_t ti = 0;
+    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++ti) {
+      const int64_t mt = tile / g.n_tiles;
+      const int nt = int(tile - mt * g.n_tiles);
+      const int w = tile_width(n_pad, nt);
+      const uint32_t acc = ti & 1;
+      // the derivative operand of this warp's first chunk is requested before the wait on the accumulator
+      YPrev y_cur;
+      load_yprev<EPI>(g.epi, y_cur, lane, mt * TM + (warp & 3) * 32, nt * NT + (warp >> 2) * CH, vec_y);
+      mbar_wait(bar_tfull + 8 * acc, (ti >> 1) & 1);
+      tc_fence_after();
+      epilogue_tile<EPI>(g.epi, tmem + acc * NT, w, stg, warp, lane, mt * TM, nt * NT, vec_ok, vec_y, y_cur, [&]() {
+        tc_fence_before();
+        mbar_arrive(bar_tempty + 8 * acc);
+      });
     }
-  }
-
-  // ---- epilogue: TMEM -> registers -> global --------------------------------------------------
-  mbar_wait(smem_u32(&bars[2]), 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const int q = warp & 3;                       // TMEM lane quarter this warp may access
-  const int half = warp >> 2;                   // warps w and w+4 share a quarter: split the column chunks
-  const int64_t gm = m0 + q * 32 + lane;
-  const int nchunks = (nrows_b + 31) / 32;
-  for (int c = half; c < nchunks; c += 2) {
-    uint32_t v[32];
-    const uint32_t taddr = tmem_d + (uint32_t(q * 32) << 16) + uint32_t(c * 32);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (gm < g.M) {
+  } else if (warp < EPI_WARPS + PROD_WARPS) {
+    // ================= producers: A (global fp32) -> hi/lo -> swizzled shared memory =================
+    const int p = t - EPI_WARPS * 32;
+    const int c = p & 7, r_base = p >> 3;
+    const bool vec = ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
+    float4 v[4];
+    int64_t tile = blockIdx.x;
+    int kb = 0;
+    if (tile < g.total_tiles) {
+      const int64_t m0 = (tile / g.n_tiles) * TM;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int64_t gn = n0 + c * 32 + j;
-        if (gn < g.N) {
-          float x = __uint_as_float(v[j]);
-          if (EPI == TC_EPI_FWD) {
-            if (g.bias) x += __ldg(g.bias + gn);
-            g.C[gm * g.ldc + gn] = tc_act_fwd(x, g.act, g.act_param);
-          } else if (EPI == TC_EPI_DGRAD) {
-            if (g.yprev) x *= tc_act_bwd_from_y(__ldg(g.yprev + gm * g.ld_yprev + gn), g.act_prev, g.act_prev_param);
-            g.C[gm * g.ldc + gn] = x;
-          } else {
-            atomicAdd(g.C + gm * g.ldc + gn, x);
-          }
+      for (int i = 0; i < 4; ++i) v[i] = load4(g.A, g.lda, m0 + r_base + 32 * i, g.M, c * 4, g.K, vec);
+    }
+    uint32_t it = 0;
+    while (tile < g.total_tiles) {
+      const uint32_t s = it % S;
+      mbar_wait(bar_empty + 8 * s, ((it / S) & 1) ^ 1);
+      uint8_t* a_hi = smem + s * STAGE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r_base + 32 * i;
+        split_store4<NPARTS>(a_hi, a_hi + PART, uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4), v[i]);
+      }
+      fence_async_smem();
+      mbar_arrive(bar_full + 8 * s);
+      ++it;
+      if (++kb == g.nkb) { kb = 0; tile += gridDim.x; }
+      if (tile < g.total_tiles) {
+        const int64_t m0 = (tile / g.n_tiles) * TM;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = load4(g.A, g.lda, m0 + r_base + 32 * i, g.M, kb * TK + c * 4, g.K, vec);
+      }
+    }
+  } else if (warp == EPI_WARPS + PROD_WARPS) {
+    // ================= B loader: one bulk async copy per k-block =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const int nt = int(tile % g.n_tiles);
+        const int w = tile_width(n_pad, nt);
+        const uint32_t bytes = uint32_t(NPARTS * w * 128);
+        const float* src = g.Bp + int64_t(nt) * NT * TK * g.nkb * NPARTS;
+        for (int kb = 0; kb < g.nkb; ++kb, ++it) {
+          const uint32_t s = it % S;
+          mbar_wait(bar_empty + 8 * s, ((it / S) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
+          bulk_g2s(smem_u32(smem + s * STAGE + NPARTS * PART), src + int64_t(kb) * NPARTS * w * TK, bytes, bar_full + 8 * s);
         }
       }
     }
+  } else {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      uint32_t it = 0, ti = 0;
+      for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++ti) {
+        const int nt = int(tile % g.n_tiles);
+        const int w = tile_width(n_pad, nt);
+        const uint32_t idesc = make_idesc_tf32(w, false);
+        const uint32_t acc = ti & 1;
+        mbar_wait(bar_tempty + 8 * acc, ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem + acc * NT;
+        for (int kb = 0; kb < g.nkb; ++kb, ++it) {
+          const uint32_t s = it % S;
+          mbar_wait(bar_full + 8 * s, (it / S) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + s * STAGE);
+          const uint32_t b_hi = a_hi + NPARTS * PART;
+          const uint64_t dah = make_desc(a_hi, 16, 1024), dal = make_desc(a_hi + PART, 16, 1024);
+          const uint64_t dbh = make_desc(b_hi, 16, 1024), dbl = make_desc(b_hi + w * 128, 16, 1024);
+          const int ksteps = kb == g.nkb - 1 ? last_ksteps : TK / 8;
+          for (int j = 0; j < ksteps; ++j) {
+            const uint64_t adv = uint64_t(j * 2);   // 8 tf32 = 32 bytes along K inside the swizzle row
+            if (NPARTS == 2) {
+              umma_tf32(d, dal + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
+              umma_tf32(d, dah + adv, dbl + adv, idesc, 1u);
+              umma_tf32(d, dah + adv, dbh + adv, idesc, 1u);
+            } else {
+              umma_tf32(d, dah + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
+            }
+          }
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_tfull + 8 * acc);
+      }
+    }
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
 
-template <bool A_KC, bool B_KC, int EPI>
-static int launch_tc(const TcArgs& g, dim3 grid, cudaStream_t s, const char* what) {
-  static bool configured = false;
-  auto kern = tc_gemm_kernel<A_KC, B_KC, EPI>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
-      return MMSB_E_CUDA;
+// ---- weight gradient ------------------------------------------------------------------------------------------
+struct WgradArgs {
+  const float* dz; int64_t lddz; int out_dim;
+  const float* x; int64_t ldx; int in_dim;
+  float* dw; int64_t lddw; float* db;
+  int64_t rows; int64_t rows_per_split; int n_tiles;
+};
+
+template <int NPARTS>
+__global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const WgradArgs g) {
+  constexpr int S = num_stages(NPARTS);
+  constexpr int STAGE = stage_bytes(NPARTS);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* stg_all = reinterpret_cast<float*>(smem + S * STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * STAGE + STG_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * MAX_STAGES);
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int mt = blockIdx.x / g.n_tiles, nt = blockIdx.x % g.n_tiles;
+  const int m0 = mt * TM, n0 = nt * NT;
+  const int w = tile_width(pad16(g.in_dim), nt);       // accumulator width (multiple of 16)
+  const int cpr = (w + 31) / 32 * 8;                   // 16-byte chunks per staged row of x (whole 32-wide panels)
+  const int b_part = cpr * 16 * TK;                    // bytes of one B part: panels x 4096
+  const int64_t k_beg = int64_t(blockIdx.y) * g.rows_per_split;
+  const int64_t k_end = min(g.rows, k_beg + g.rows_per_split);
+  const int nkb = k_beg < k_end ? int((k_end - k_beg + TK - 1) / TK) : 0;
+
+  if (t == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8 * s, PROD_THREADS);
+      mbar_init(bar_empty + 8 * s, 1);
     }
+    mbar_init(bar_tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp < EPI_WARPS) {
+      // ================= epilogue: partial tile -> dW with coalesced reductions =================
+      float* stg = stg_all + warp * 32 * STG_LD;
+      EpiArgs e{};
+      e.C = g.dw; e.ldc = g.lddw; e.M = g.out_dim; e.N = g.in_dim;
+      mbar_wait(bar_tfull, 0);
+      tc_fence_after();
+      YPrev y_none;
+      epilogue_tile<EPI_ATOMIC>(e, tmem, w, stg, warp, lane, m0, n0, false, false, y_none, []() {});
+    } else if (warp < EPI_WARPS + PROD_WARPS) {
+      // ================= producers: dz and x rows -> hi/lo -> MN-major swizzled shared memory =================
+      const int p = t - EPI_WARPS * 32;
+      const int ca = p & 31, ka = p >> 5;     // dz tile: 32 chunks per row, rows ka + 8 i
+      const int cb = p & 63, kbb = p >> 6;    // x tile : up to 64 chunks per row, rows kbb + 4 i
+      const bool vec_a = ((g.lddz & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.dz) & 15) == 0);
+      const bool vec_b = ((g.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.x) & 15) == 0);
+      const bool b_active = cb < cpr;
+      const bool want_db = g.db != nullptr && nt == 0;
+      float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 va[4], vb[8];
+      auto load_block = [&](int kb) {
+        const int64_t k0 = k_beg + int64_t(kb) * TK;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) va[i] = load4(g.dz, g.lddz, k0 + ka + 8 * i, k_end, m0 + ca * 4, g.out_dim, vec_a);
+        if (b_active) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vb[i] = load4(g.x, g.ldx, k0 + kbb + 4 * i, k_end, n0 + cb * 4, g.in_dim, vec_b);
+        }
+      };
+      load_block(0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const uint32_t s = kb % S;
+        mbar_wait(bar_empty + 8 * s, ((kb / S) & 1) ^ 1);
+        uint8_t* a_hi = smem + s * STAGE;
+        uint8_t* b_hi = a_hi + NPARTS * PART;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int k = ka + 8 * i;
+          split_store4<NPARTS>(a_hi, a_hi + PART, mn_offset(ca, k), va[i]);
+          colsum.x += va[i].x; colsum.y += va[i].y; colsum.z += va[i].z; colsum.w += va[i].w;
+        }
+        if (b_active) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int k = kbb + 4 * i;
+            split_store4<NPARTS>(b_hi, b_hi + b_part, mn_offset(cb, k), vb[i]);
+          }
+        }
+        fence_async_smem();
+        mbar_arrive(bar_full + 8 * s);
+        if (kb + 1 < nkb) load_block(kb + 1);
+      }
+      if (want_db) {
+        // the 8 producer warps hold partial column sums for the same 128 columns: combine through the L2
+        const int col = m0 + ca * 4;
+        if (col < g.out_dim) atomicAdd(g.db + col, colsum.x);
+        if (col + 1 < g.out_dim) atomicAdd(g.db + col + 1, colsum.y);
+        if (col + 2 < g.out_dim) atomicAdd(g.db + col + 2, colsum.z);
+        if (col + 3 < g.out_dim) atomicAdd(g.db + col + 3, colsum.w);
+      }
+    } else if (warp == EPI_WARPS + PROD_WARPS + 1) {
+      // ================= MMA issuer =================
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_tf32(w, true);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint32_t s = kb % S;
+          mbar_wait(bar_full + 8 * s, (kb / S) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + s * STAGE);
+          const uint32_t b_hi = a_hi + NPARTS * PART;
+          const uint64_t dah = make_desc(a_hi, 4096, 512, 1), dal = make_desc(a_hi + PART, 4096, 512, 1);
+          const uint64_t dbh = make_desc(b_hi, 4096, 512, 1), dbl = make_desc(b_hi + b_part, 4096, 512, 1);
+          // rows past k_end were staged as zeros, so every k-step of the last block may be issued
+#pragma unroll
+          for (int j = 0; j < TK / 8; ++j) {
+            const uint64_t adv = uint64_t(j * (1024 >> 4));   // 8 k-rows = one 1024-byte atom
+            if (NPARTS == 2) {
+              umma_tf32(tmem, dal + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
+              umma_tf32(tmem, dah + adv, dbl + adv, idesc, 1u);
+              umma_tf32(tmem, dah + adv, dbh + adv, idesc, 1u);
+            } else {
+              umma_tf32(tmem, dah + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
+            }
+          }
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_tfull);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+  }
+}
+
+template <typename K>
+static int set_smem(K kern, int bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
+    return MMSB_E_CUDA;
+  }
+  return MMSB_OK;
+}
+
+template <int NPARTS, int EPI>
+static int launch_rows(const RowsArgs& g, cudaStream_t s, const char* what) {
+  static bool configured = false;
+  auto kern = tc_rows_kernel<NPARTS, EPI>;
+  if (!configured) {
+    int rc = set_smem(kern, smem_bytes(NPARTS), what);
+    if (rc) return rc;
     configured = true;
   }
-  kern<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(g);
+  const int64_t grid = g.total_tiles < kNumSMs ? g.total_tiles : kNumSMs;
+  kern<<<(unsigned)grid, THREADS, smem_bytes(NPARTS), s>>>(g);
   return check_launch(what);
 }
 
-static int pick_bn(int64_t n) {
-  int64_t r = ((n + 15) / 16) * 16;
-  return int(r > 256 ? 256 : r);
+template <int NPARTS>
+static int launch_wgrad(const WgradArgs& g, dim3 grid, cudaStream_t s, const char* what) {
+  static bool configured = false;
+  auto kern = tc_wgrad_kernel<NPARTS>;
+  if (!configured) {
+    int rc = set_smem(kern, smem_bytes(NPARTS), what);
+    if (rc) return rc;
+    configured = true;
+  }
+  kern<<<grid, THREADS, smem_bytes(NPARTS), s>>>(g);
+  return check_launch(what);
 }
 
-// ---- entry points used by mlp_simt.cu's dispatcher ---------------------------------------------
-int tc_linear_fwd(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int64_t n,
-                  int in_dim, int out_dim, int act, float act_param, cudaStream_t s) {
-  TcArgs g{};
-  g.A = x; g.lda = ldx; g.B = w; g.ldb = in_dim; g.C = y; g.ldc = ldy;
-  g.M = n; g.N = out_dim; g.K = in_dim; g.bias = b; g.act = act; g.act_param = act_param;
-  g.k_per_split = in_dim; g.bn = pick_bn(out_dim);
-  dim3 grid((unsigned)ceil_div(n, TM), (unsigned)ceil_div(out_dim, g.bn), 1);
-  return launch_tc<true, true, TC_EPI_FWD>(g, grid, s, "linear_fwd(tcgen05)");
-}
-
-int tc_linear_bwd_data(const float* dz, int64_t lddz, const float* w, float* dx, int64_t lddx, const float* y_prev,
-                       int64_t ld_yprev, int act_prev, float act_prev_param, int64_t n, int in_dim, int out_dim,
-                       cudaStream_t s) {
-  TcArgs g{};
-  g.A = dz; g.lda = lddz; g.B = w; g.ldb = in_dim; g.C = dx; g.ldc = lddx;
-  g.M = n; g.N = in_dim; g.K = out_dim;
-  g.yprev = y_prev; g.ld_yprev = ld_yprev; g.act_prev = act_prev; g.act_prev_param = act_prev_param;
-  g.k_per_split = out_dim; g.bn = pick_bn(in_dim);
-  dim3 grid((unsigned)ceil_div(n, TM), (unsigned)ceil_div(in_dim, g.bn), 1);
-  return launch_tc<true, false, TC_EPI_DGRAD>(g, grid, s, "linear_bwd_data(tcgen05)");
-}
-
-int tc_linear_bwd_weight(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw, int64_t n, int in_dim,
-                         int out_dim, cudaStream_t s) {
-  TcArgs g{};
-  g.A = dz; g.lda = lddz; g.B = x; g.ldb = ldx; g.C = dw; g.ldc = in_dim;
-  g.M = out_dim; g.N = in_dim; g.K = n; g.bn = pick_bn(in_dim);
-  const int64_t tiles = ceil_div(out_dim, TM) * ceil_div(in_dim, g.bn);
-  int64_t splits = ceil_div(int64_t(2) * kNumSMs, tiles);
-  const int64_t max_splits = ceil_div(n, 4 * TK);
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  int64_t kps = ceil_div(ceil_div(n, splits), TK) * TK;
-  g.k_per_split = kps;
-  dim3 grid((unsigned)ceil_div(out_dim, TM), (unsigned)ceil_div(in_dim, g.bn), (unsigned)ceil_div(n, kps));
-  return launch_tc<false, false, TC_EPI_ATOMIC>(g, grid, s, "linear_bwd_weight(tcgen05)");
-}
-
+}  // namespace tc
 }  // namespace mmsb
+
+using namespace mmsb;
+
+static bool valid_precision(int p) { return p == 1 || p == 3; }
+
+extern "C" int64_t mmsb_linear_packed_size(int32_t n_dim, int32_t k_dim, int32_t precision) {
+  if (n_dim <= 0 || k_dim <= 0 || !valid_precision(precision)) return -1;
+  return tc::packed_floats(n_dim, k_dim, precision == 3 ? 2 : 1);
+}
+
+extern "C" int mmsb_linear_pack_weight(const float* w, int64_t ldw, int32_t out_dim, int32_t in_dim, int32_t transpose,
+                                       int32_t precision, float* packed, mmsb_stream_t stream) {
+  MMSB_REQUIRE(w && packed, "linear_pack_weight: null pointer");
+  MMSB_REQUIRE(out_dim > 0 && in_dim > 0 && ldw >= in_dim, "linear_pack_weight: bad shape out=%d in=%d ldw=%lld", out_dim,
+               in_dim, (long long)ldw);
+  MMSB_REQUIRE(valid_precision(precision), "linear_pack_weight: precision must be 1 (TF32) or 3 (3xTF32), got %d", precision);
+  const int n = transpose ? in_dim : out_dim, k = transpose ? out_dim : in_dim;
+  const int64_t total = int64_t(tc::pad16(n)) * ((k + tc::TK - 1) / tc::TK) * tc::TK;
+  const int blocks = int(ceil_div(total, 256) < 4 * kNumSMs ? ceil_div(total, 256) : 4 * kNumSMs);
+  tc::pack_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, ldw, n, k, transpose, precision == 3 ? 2 : 1, packed);
+  return check_launch("linear_pack_weight");
+}
+
+extern "C" int mmsb_linear_fwd_tc(const float* x, int64_t ldx, const float* packed_w, const float* b, float* y, int64_t ldy,
+                                  int64_t n, int32_t in_dim, int32_t out_dim, int32_t act, float act_param, int32_t precision,
+                                  mmsb_stream_t stream) {
+  MMSB_REQUIRE(x && packed_w && y, "linear_fwd_tc: null pointer");
+  MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && ldx >= in_dim && ldy >= out_dim, "linear_fwd_tc: bad shape");
+  MMSB_REQUIRE(act >= MMSB_ACT_NONE && act <= MMSB_ACT_SIGMOID, "linear_fwd_tc: unknown activation %d", act);
+  MMSB_REQUIRE(valid_precision(precision), "linear_fwd_tc: precision must be 1 or 3, got %d", precision);
+  if (n == 0) return MMSB_OK;
+  tc::RowsArgs g{};
+  g.A = x; g.lda = ldx; g.M = n; g.K = in_dim; g.Bp = packed_w; g.N = out_dim;
+  g.epi.C = y; g.epi.ldc = ldy; g.epi.M = n; g.epi.N = out_dim; g.epi.bias = b; g.epi.act = act; g.epi.act_param = act_param;
+  g.n_tiles = int(ceil_div(tc::pad16(out_dim), tc::NT)); g.nkb = int(ceil_div(in_dim, tc::TK));
+  g.total_tiles = ceil_div(n, tc::TM) * g.n_tiles;
+  return precision == 3 ? tc::launch_rows<2, tc::EPI_FWD>(g, as_stream(stream), "linear_fwd_tc(3xTF32)")
+                        : tc::launch_rows<1, tc::EPI_FWD>(g, as_stream(stream), "linear_fwd_tc(TF32)");
+}
+
+extern "C" int mmsb_linear_bwd_data_tc(const float* dz, int64_t lddz, const float* packed_wt, float* dx, int64_t lddx,
+                                       const float* y_prev, int64_t ld_yprev, int32_t act_prev, float act_prev_param,
+                                       int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision, mmsb_stream_t stream) {
+  MMSB_REQUIRE(dz && packed_wt && dx, "linear_bwd_data_tc: null pointer");
+  MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && lddz >= out_dim && lddx >= in_dim, "linear_bwd_data_tc: bad shape");
+  MMSB_REQUIRE(valid_precision(precision), "linear_bwd_data_tc: precision must be 1 or 3, got %d", precision);
+  if (n == 0) return MMSB_OK;
+  tc::RowsArgs g{};
+  g.A = dz; g.lda = lddz; g.M = n; g.K = out_dim; g.Bp = packed_wt; g.N = in_dim;
+  g.epi.C = dx; g.epi.ldc = lddx; g.epi.M = n; g.epi.N = in_dim;
+  g.epi.yprev = y_prev; g.epi.ld_yprev = ld_yprev; g.epi.act_prev = act_prev; g.epi.act_prev_param = act_prev_param;
+  g.n_tiles = int(ceil_div(tc::pad16(in_dim), tc::NT)); g.nkb = int(ceil_div(out_dim, tc::TK));
+  g.total_tiles = ceil_div(n, tc::TM) * g.n_tiles;
+  return precision == 3 ? tc::launch_rows<2, tc::EPI_DGRAD>(g, as_stream(stream), "linear_bwd_data_tc(3xTF32)")
+                        : tc::launch_rows<1, tc::EPI_DGRAD>(g, as_stream(stream), "linear_bwd_data_tc(TF32)");
+}
+
+extern "C" int mmsb_linear_bwd_weight_tc(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw, float* db,
+                                         int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision,
+                                         mmsb_stream_t stream) {
+  MMSB_REQUIRE(dz && x && dw, "linear_bwd_weight_tc: null pointer");
+  MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && lddz >= out_dim && ldx >= in_dim, "linear_bwd_weight_tc: bad shape");
+  MMSB_REQUIRE(valid_precision(precision), "linear_bwd_weight_tc: precision must be 1 or 3, got %d", precision);
+  if (n == 0) return MMSB_OK;
+  tc::WgradArgs g{};
+  g.dz = dz; g.lddz = lddz; g.out_dim = out_dim; g.x = x; g.ldx = ldx; g.in_dim = in_dim;
+  g.dw = dw; g.lddw = in_dim; g.db = db; g.rows = n;
+  const int m_tiles = int(ceil_div(out_dim, tc::TM));
+  g.n_tiles = int(ceil_div(tc::pad16(in_dim), tc::NT));
+  const int tiles = m_tiles * g.n_tiles;
+  int64_t splits = kNumSMs / tiles;
+  if (splits < 1) splits = 1;
+  const int64_t max_splits = ceil_div(n, 4 * tc::TK);
+  if (splits > max_splits) splits = max_splits;
+  g.rows_per_split = ceil_div(ceil_div(n, splits), tc::TK) * tc::TK;
+  dim3 grid((unsigned)tiles, (unsigned)ceil_div(n, g.rows_per_split));
+  return precision == 3 ? tc::launch_wgrad<2>(g, grid, as_stream(stream), "linear_bwd_weight_tc(3xTF32)")
+                        : tc::launch_wgrad<1>(g, grid, as_stream(stream), "linear_bwd_weight_tc(TF32)");
+}

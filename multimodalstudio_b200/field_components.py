@@ -299,6 +299,7 @@ class FeatureGrid(FieldComponent):
         self.output_dim = self.encoding.get_out_dim()
         self.hash_encoding_mask = torch.ones(
             self.config.encoding.num_levels * self.config.encoding.features_per_level, dtype=torch.float32)
+        self.active_level = self.config.encoding.num_levels
 
     def _mask_on(self, device):
         if self.hash_encoding_mask.device != device:
@@ -309,6 +310,7 @@ class FeatureGrid(FieldComponent):
         return self.encoding(input_tensor, radius=float(self.radius), mask=self._mask_on(input_tensor.device))
 
     def update_mask(self, level: int):
+        self.active_level = int(level)
         self.hash_encoding_mask[:] = 1.0
         self.hash_encoding_mask[level * self.config.encoding.features_per_level:] = 0
 
@@ -402,7 +404,7 @@ def mueller_rotate(theta):
 
 def align_polarization_filters(stokes_vectors, directions, camera_up_directions):
     """ref: polarizer.py:54-82"""
-    z = torch.tensor([0.0, 0.0, 1.0], device=directions.device, dtype=directions.dtype)[None].expand(directions.shape)
+    z = ops.const_tensor("z_axis", lambda: torch.tensor([0.0, 0.0, 1.0]), directions.device)[None].expand(directions.shape)
     normal = torch.nn.functional.normalize(torch.linalg.cross(directions, z), dim=-1)
     cos_theta = torch.clamp(torch.sum(normal * camera_up_directions, dim=-1), min=-1 + 1e-4, max=1 - 1e-4)
     theta = torch.acos(cos_theta) - np.pi / 2
@@ -411,8 +413,8 @@ def align_polarization_filters(stokes_vectors, directions, camera_up_directions)
 
 def stokes_to_intensity(stokes_vectors):
     """ref: polarizer.py:84-101"""
-    m = 0.5 * torch.tensor([[1.0, 1.0, 0.0], [1.0, 0.0, 1.0], [1.0, -1.0, 0.0], [1.0, 0.0, -1.0]],
-                           dtype=stokes_vectors.dtype, device=stokes_vectors.device)
+    m = ops.const_tensor("stokes2int", lambda: 0.5 * torch.tensor([[1.0, 1.0, 0.0], [1.0, 0.0, 1.0], [1.0, -1.0, 0.0],
+                                                                     [1.0, 0.0, -1.0]]), stokes_vectors.device)
     return (m[None] @ stokes_vectors[..., None]).squeeze(-1)
 
 

@@ -207,7 +207,7 @@ class PDFSampler(Sampler):
 
     def make_u(self, num_rays, num_samples, device, rand=None):
         num_bins = num_samples + 1
-        u = torch.linspace(0.0, 1.0 - (1.0 / num_bins), steps=num_bins).to(device)
+        u = ops.const_tensor(("pdf_u", num_bins), lambda: torch.linspace(0.0, 1.0 - (1.0 / num_bins), steps=num_bins), device)
         if self.config.train_stratified and self.training:
             u = u.expand(num_rays, num_bins)
             if rand is None:
@@ -378,7 +378,8 @@ class SurfaceModel(nn.Module):
         sdf, geo_feature = self.surface_field(inputs)
         # 4 tetrahedron taps, sdf only (surface_model.py:138-146)
         delta = self.numerical_gradients_delta / np.sqrt(3)
-        k = torch.tensor([[1, -1, -1], [-1, -1, 1], [-1, 1, -1], [1, 1, 1]], dtype=inputs.dtype, device=inputs.device)
+        k = ops.const_tensor("taps4", lambda: torch.tensor([[1, -1, -1], [-1, -1, 1], [-1, 1, -1], [1, 1, 1]], dtype=torch.float32),
+                             inputs.device)
         taps = (inputs[None] + k[:, None, :] * delta).reshape(-1, 3)
         sdf_t = self.surface_field.single_output(taps).reshape(4, n)
         want_h = bool(self.training and self.config.compute_hessian)
@@ -789,6 +790,12 @@ class LossManager:
             setattr(self, element, self.config.radiance_losses[element].setup(num_iterations=num_iterations, **kwargs))
         for element, cfg in self.config.geometry_losses.items():
             setattr(self, element, cfg.setup(num_iterations=num_iterations, **kwargs))
+
+    def weights(self, step):
+        """Loss weights in effect at `step` (the step-dependent scalars compute_loss multiplies in)."""
+        out = [getattr(self, mod)._weight(step) for mod in self.modalities]
+        out += [getattr(self, name)._weight(step) for name in self.config.geometry_losses]
+        return out
 
     def compute_loss(self, outputs, targets, pixel_coords, step, eval_step=False, mosaick_patterns=None):
         losses = {}

@@ -4,6 +4,8 @@ all arithmetic runs in libmms_b200.so.  Non-CUDA tensors raise (no fallback).
 """
 import ctypes
 import math
+import os
+import weakref
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -11,6 +13,20 @@ import torch
 
 from . import _lib
 from ._lib import MmsbHashGridDesc, call, ptr, stream_ptr
+
+_CONST_CACHE = {}
+
+
+def const_tensor(key, make, device):
+    """Small device constants (tap offsets, Mueller matrices, linspaces): built once per device — a host-to-device
+    copy inside the step would break CUDA-graph capture."""
+    k = (key, str(device))
+    t = _CONST_CACHE.get(k)
+    if t is None:
+        t = make().to(device)
+        _CONST_CACHE[k] = t
+    return t
+
 
 ACT = {"None": 0, None: 0, "ReLU": 1, "Softplus": 2, "Sigmoid": 3}
 INTERP = {"Linear": 0, None: 0, "Smoothstep": 1}
@@ -198,6 +214,83 @@ def linear_fwd(x, w, b, act, act_param, out=None):
     return out
 
 
+def pack_weight(w, transpose: bool, precision: int):
+    """Pre-split / pre-swizzled operand of the tcgen05 layer kernels (mmsb_linear_pack_weight)."""
+    o, k = w.shape
+    n_dim, k_dim = (k, o) if transpose else (o, k)
+    size = int(_lib.load_library().mmsb_linear_packed_size(n_dim, k_dim, precision))
+    if size < 0:
+        raise ValueError(f"pack_weight: bad arguments {tuple(w.shape)} precision {precision}")
+    packed = torch.empty((size,), device=w.device, dtype=torch.float32)
+    call("mmsb_linear_pack_weight", ptr(w), _i64(w.stride(0)), _i32(o), _i32(k), _i32(1 if transpose else 0),
+         _i32(precision), ptr(packed), stream_ptr())
+    return packed
+
+
+def linear_fwd_tc(x, packed_w, b, out_dim, act, act_param, precision, out=None):
+    n, k = x.shape
+    if out is None:
+        out = torch.empty((n, out_dim), device=x.device, dtype=torch.float32)
+    call("mmsb_linear_fwd_tc", ptr(x), _i64(x.stride(0)), ptr(packed_w), ptr(b), ptr(out), _i64(out.stride(0)), _i64(n),
+         _i32(k), _i32(out_dim), _i32(act), _f32(act_param), _i32(precision), stream_ptr())
+    return out
+
+
+def linear_bwd_data_tc(dz, packed_wt, in_dim, y_prev, act_prev, act_param, precision, out=None):
+    n, o = dz.shape
+    if out is None:
+        out = torch.empty((n, in_dim), device=dz.device, dtype=torch.float32)
+    call("mmsb_linear_bwd_data_tc", ptr(dz), _i64(dz.stride(0)), ptr(packed_wt), ptr(out), _i64(out.stride(0)),
+         ptr(y_prev), _i64(y_prev.stride(0) if y_prev is not None else 0), _i32(act_prev), _f32(act_param), _i64(n),
+         _i32(in_dim), _i32(o), _i32(precision), stream_ptr())
+    return out
+
+
+def linear_bwd_weight_tc(dz, x, dw, db, precision):
+    n, o = dz.shape
+    k = x.shape[1]
+    call("mmsb_linear_bwd_weight_tc", ptr(dz), _i64(dz.stride(0)), ptr(x), _i64(x.stride(0)), ptr(dw), ptr(db), _i64(n),
+         _i32(k), _i32(o), _i32(precision), stream_ptr())
+
+# MLP arithmetic mode of the wide layers: 3 = tcgen05 3xTF32 (fp32-accurate, default), 1 = tcgen05 single-pass TF32
+# (1e-2 band, the precision class of the reference's fp16-autocast GPU runs), 0 = fp32 SIMT GEMM.
+MLP_PRECISION = int(os.environ.get("MMSB_MLP_PRECISION", "3"))
+_PACK_CACHE = {}
+
+
+def set_mlp_precision(precision: int) -> None:
+    global MLP_PRECISION
+    if precision not in (0, 1, 3):
+        raise ValueError("MLP precision must be 0 (fp32 SIMT), 1 (TF32) or 3 (3xTF32)")
+    MLP_PRECISION = precision
+    _PACK_CACHE.clear()
+
+
+def clear_pack_cache() -> None:
+    """Call after every optimiser step (the packed operands are functions of the weights)."""
+    _PACK_CACHE.clear()
+
+
+def _use_tc(w) -> bool:
+    # every layer, also the narrow ones (sdf-only column, modality heads): the centre and tap evaluations of the SDF
+    # must share one arithmetic, otherwise the finite differences (Hessian ~ 1/delta^2) amplify the path difference
+    return MLP_PRECISION != 0
+
+
+def packed_weight(w, transpose: bool, precision: int):
+    """Packed operand of w, memoised per tensor object and version (valid while torch.nn.utils.parametrize.cached()
+    keeps the effective weight alive, i.e. for one step)."""
+    key = (id(w), bool(transpose), precision)
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0]() is w and hit[1] == w._version:
+        return hit[2]
+    packed = pack_weight(_f(w.detach()), transpose, precision)
+    if len(_PACK_CACHE) > 512:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = (weakref.ref(w), w._version, packed)
+    return packed
+
+
 class MLPFn(torch.autograd.Function):
     """y = MLP(x): layers [(W_i [out,in], b_i)], hidden activation, output activation, optional
     skip connections (the layer input becomes cat([h, x]) / sqrt(2), mlp.py:164-165).
@@ -210,6 +303,7 @@ class MLPFn(torch.autograd.Function):
         nl = len(params) // 2
         in_dim = x.shape[-1]
         x2 = _rows(x, in_dim)
+        prec = MLP_PRECISION if not skips else 0
         ws = [_f(params[2 * i]) for i in range(nl)]
         bs = [_f(params[2 * i + 1]) if params[2 * i + 1] is not None else None for i in range(nl)]
         if n_out_used is not None:
@@ -217,14 +311,24 @@ class MLPFn(torch.autograd.Function):
             bs[-1] = bs[-1][:n_out_used].contiguous() if bs[-1] is not None else None
         acts_in = [x2]       # input of every layer
         h = x2
+        need_grad = any(ctx.needs_input_grad)
+        packed_t = [None] * nl   # W^T operands of the dgrad products (packed once per step, see packed_weight)
         for i in range(nl):
             if i in skips:
                 h = torch.cat([h, x2], -1) / math.sqrt(2)
                 acts_in[i] = h
             a = hidden_act if i < nl - 1 else out_act
-            h = linear_fwd(h, ws[i], bs[i], a, act_param)
+            if prec != 0 and _use_tc(ws[i]):
+                src = params[2 * i] if (n_out_used is None or i < nl - 1) else ws[i]
+                h = linear_fwd_tc(h, packed_weight(src, False, prec), bs[i], ws[i].shape[0], a, act_param, prec)
+                if need_grad and (i > 0 or ctx.needs_input_grad[0]):
+                    packed_t[i] = packed_weight(src, True, prec)
+            else:
+                h = linear_fwd(h, ws[i], bs[i], a, act_param)
             acts_in.append(h)
         ctx.save_for_backward(*acts_in, *ws)
+        ctx.prec = prec
+        ctx.packed_t = packed_t
         ctx.cfg = (nl, hidden_act, act_param, out_act, tuple(skips), n_out_used, x.shape, in_dim,
                    [p is not None for p in params], [tuple(params[2 * i].shape) for i in range(nl)])
         return h.reshape(*x.shape[:-1], h.shape[-1])
@@ -232,6 +336,7 @@ class MLPFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         nl, hidden_act, act_param, out_act, skips, n_out_used, x_shape, in_dim, has, wshapes = ctx.cfg
+        prec = ctx.prec
         saved = ctx.saved_tensors
         acts = saved[: nl + 1]
         ws = saved[nl + 1:]
@@ -252,11 +357,15 @@ class MLPFn(torch.autograd.Function):
             w = ws[i]
             o, k = w.shape
             xin = acts[i]
+            tc = prec != 0 and _use_tc(w)
             if ctx.needs_input_grad[6 + 2 * i] or (has[2 * i + 1] and ctx.needs_input_grad[7 + 2 * i]):
                 dw = torch.zeros((o, k), device=w.device, dtype=torch.float32)
                 db = torch.zeros((o,), device=w.device, dtype=torch.float32) if has[2 * i + 1] else None
-                call("mmsb_linear_bwd_weight", ptr(dz), _i64(dz.stride(0)), ptr(xin), _i64(xin.stride(0)), ptr(dw),
-                     ptr(db), _i64(n), _i32(k), _i32(o), stream_ptr())
+                if tc:
+                    linear_bwd_weight_tc(dz, xin, dw, db, prec)
+                else:
+                    call("mmsb_linear_bwd_weight", ptr(dz), _i64(dz.stride(0)), ptr(xin), _i64(xin.stride(0)), ptr(dw),
+                         ptr(db), _i64(n), _i32(k), _i32(o), stream_ptr())
                 if i == nl - 1 and n_out_used is not None:
                     full_w = torch.zeros(wshapes[i], device=w.device, dtype=torch.float32)
                     full_w[:n_out_used] = dw
@@ -272,9 +381,13 @@ class MLPFn(torch.autograd.Function):
             dxin = torch.empty((n, k), device=w.device, dtype=torch.float32)
             # the input of layer i is the hidden activation of layer i-1 (unless a skip concat sits between)
             fuse_prev = i > 0 and i not in skips
-            call("mmsb_linear_bwd_data", ptr(dz), _i64(dz.stride(0)), ptr(w), ptr(dxin), _i64(k),
-                 ptr(xin) if fuse_prev else None, _i64(xin.stride(0)), _i32(hidden_act if fuse_prev else 0),
-                 _f32(act_param), _i64(n), _i32(k), _i32(o), stream_ptr())
+            if tc:
+                linear_bwd_data_tc(dz, ctx.packed_t[i], k, xin if fuse_prev else None,
+                                   hidden_act if fuse_prev else 0, act_param, prec, out=dxin)
+            else:
+                call("mmsb_linear_bwd_data", ptr(dz), _i64(dz.stride(0)), ptr(w), ptr(dxin), _i64(k),
+                     ptr(xin) if fuse_prev else None, _i64(xin.stride(0)), _i32(hidden_act if fuse_prev else 0),
+                     _f32(act_param), _i64(n), _i32(k), _i32(o), stream_ptr())
             if i in skips:
                 dxin = dxin / math.sqrt(2)
                 hk = k - in_dim
@@ -666,3 +779,9 @@ def sumsq(x, out):
 def adamw_step(param, grad, exp_avg, exp_avg_sq, grad_scale, lr, beta1, beta2, eps, weight_decay, step):
     call("mmsb_adamw_step", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(grad_scale), _f32(lr), _f32(beta1),
          _f32(beta2), _f32(eps), _f32(weight_decay), _i32(step), _i64(param.numel()), stream_ptr())
+
+
+def adamw_step_dev(param, grad, exp_avg, exp_avg_sq, grad_sumsq, max_norm, hyper, beta1, beta2, eps, weight_decay):
+    """hyper: device tensor [3] = {lr, 1 - beta1^t, sqrt(1 - beta2^t)} (graph-replayable AdamW)."""
+    call("mmsb_adamw_step_dev", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(grad_sumsq), _f32(max_norm or 0.0),
+         ptr(hyper), _f32(beta1), _f32(beta2), _f32(eps), _f32(weight_decay), _i64(param.numel()), stream_ptr())

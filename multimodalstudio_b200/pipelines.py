@@ -112,6 +112,9 @@ class FlatAdamW:
         self.step_count = 0
         self.sumsq = torch.zeros(1, device=dev)
         self.scale = torch.ones(1, device=dev)
+        # per-step scalars of the graph-replayable update: {lr, 1 - beta1^t, sqrt(1 - beta2^t)}
+        self.hyper = torch.zeros(3, device=dev)
+        self.hyper_host = torch.zeros(3).pin_memory() if dev.type == "cuda" else torch.zeros(3)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -127,6 +130,23 @@ class FlatAdamW:
             scale = self.scale
         ops.adamw_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, scale, self.lr * lr_factor, self.betas[0],
                        self.betas[1], self.eps, self.wd, self.step_count)
+
+
+    def advance(self, lr_factor: float = 1.0):
+        """Host side of `step_dev`: bumps the step count and uploads this step's scalars (outside any graph)."""
+        self.step_count += 1
+        self.hyper_host[0] = self.lr * lr_factor
+        self.hyper_host[1] = 1.0 - self.betas[0] ** self.step_count
+        self.hyper_host[2] = math.sqrt(1.0 - self.betas[1] ** self.step_count)
+        self.hyper.copy_(self.hyper_host, non_blocking=True)
+
+    def step_dev(self):
+        """Clip + AdamW with every step-dependent scalar read from device memory (CUDA-graph replayable)."""
+        if self.max_norm is not None:
+            self.sumsq.zero_()
+            ops.sumsq(self.grad, self.sumsq)
+        ops.adamw_step_dev(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.sumsq if self.max_norm is not None else None,
+                           self.max_norm, self.hyper, self.betas[0], self.betas[1], self.eps, self.wd)
 
 
 def multistep_warmup_factor(step, num_iterations, warm_up_ratio=0.1, milestones=(0.5, 0.75, 0.9), gamma=0.4):
@@ -168,19 +188,26 @@ class RawPipeline:
         self.callbacks = self.model.get_training_callbacks(TrainingCallbackAttributes(model=self.model, trainer=t))
         self.process_group = process_group
         self.model.train()
+        self._graph = None          # (key, static coords, static targets, fwd+bwd graph, optimizer graph, losses, total)
+        self._last_key = None
+        self.graph_launches = 0     # kernels of libmms_b200.so captured in one step's graphs
 
     def run_callbacks(self, step):
         for cb in self.callbacks:
             cb.run_callback_at_location(step, TrainingCallbackLocation.BEFORE_TRAIN_ITERATION)
 
     def forward_backward(self, coords, targets, step):
-        ray_bundles = self.ray_generator(coords)
-        outputs = self.model(ray_bundles)
+        ops.clear_pack_cache()
+        with torch.nn.utils.parametrize.cached():     # one weight-norm evaluation (and one operand pack) per step
+            ray_bundles = self.ray_generator(coords)
+            outputs = self.model(ray_bundles)
         losses, total = self.loss_manager.compute_loss(outputs, targets, coords, step, mosaick_patterns=self.patterns)
         for opt in self.optimizers.values():
             opt.zero_grad()
         total.backward()
-        return losses, total
+        # detached: a caller holding on to the losses must not keep the autograd graph (and its AccumulateGrad
+        # nodes, which remember the stream they were created on) alive into the next step / a graph capture
+        return {k: (v.detach() if torch.is_tensor(v) else v) for k, v in losses.items()}, total.detach()
 
     def all_reduce_gradients(self):
         """DDP semantics of the reference (mean over ranks) — one flat NCCL all-reduce per optimizer."""
@@ -204,3 +231,71 @@ class RawPipeline:
         self.all_reduce_gradients()
         self.optimizer_step(step)
         return losses, total
+
+    # ---- the same step replayed from CUDA graphs ------------------------------------------------------------
+    def _schedule_key(self, step, coords, targets):
+        """Everything a captured step bakes into its launch arguments: the schedule state the callbacks set
+        (level mask, delta, anneal), the loss weights of this step and the batch shapes.  lr and the AdamW bias
+        corrections are NOT baked (device scalars, FlatAdamW.advance)."""
+        sm = self.model.surface_model
+        levels = tuple(int(m.active_level) for m in self.model.modules() if hasattr(m, "active_level"))
+        weights = tuple(float(w) for w in self.loss_manager.weights(step))
+        shapes = tuple((m, tuple(c.shape), tuple(targets[m].shape)) for m, c in coords.items())
+        return (float(sm.numerical_gradients_delta), float(sm.volume_rendering._cos_anneal_ratio), levels, weights, shapes,
+                ops.MLP_PRECISION)
+
+    def train_step_graphed(self, step, coords, targets):
+        """train_step with the ~4000 launches of a step replayed from two CUDA graphs (forward + backward | clip +
+        AdamW; the NCCL all-reduce sits between them).  A step whose schedule key differs from the previous step's
+        runs eagerly (early training: the anneal ratio moves every step); the second step with the same key captures.
+        coords / targets may live in pinned host memory: they are copied into the graphs' static inputs."""
+        self.run_callbacks(step)
+        key = self._schedule_key(step, coords, targets)
+        if self._graph is None or self._graph[0] != key:
+            if self._last_key != key:
+                self._last_key = key
+                self._graph = None
+                dc = {m: c.to(self.device, non_blocking=True) for m, c in coords.items()}
+                dt = {m: t.to(self.device, non_blocking=True) for m, t in targets.items()}
+                losses, total = self.forward_backward(dc, dt, step)
+                self.all_reduce_gradients()
+                self.optimizer_step(step)
+                return losses, total
+            self._capture(key, step, coords, targets)
+        _, sc, st, g_fb, g_opt, losses, total = self._graph
+        for m in sc:
+            sc[m].copy_(coords[m], non_blocking=True)
+            st[m].copy_(targets[m], non_blocking=True)
+        f = multistep_warmup_factor(step, self.max_num_iterations)
+        for opt in self.optimizers.values():
+            opt.advance(lr_factor=f)
+        g_fb.replay()
+        self.all_reduce_gradients()
+        g_opt.replay()
+        return losses, total
+
+    def _capture(self, key, step, coords, targets):
+        from . import _lib
+        sc = {m: torch.empty(c.shape, dtype=c.dtype, device=self.device) for m, c in coords.items()}
+        st = {m: torch.empty(t.shape, dtype=t.dtype, device=self.device) for m, t in targets.items()}
+        for m in sc:
+            sc[m].copy_(coords[m])
+            st[m].copy_(targets[m])
+        # warm-up on a side stream (torch's whole-network-capture recipe): first-use initialisation
+        # (cudaFuncSetAttribute, constant caches) happens outside the capture
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.forward_backward(sc, st, step)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        l0 = _lib.launch_count()
+        g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_fb):
+            losses, total = self.forward_backward(sc, st, step)
+        g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_opt, pool=g_fb.pool()):
+            for opt in self.optimizers.values():
+                opt.step_dev()
+        self.graph_launches = _lib.launch_count() - l0
+        self._graph = (key, sc, st, g_fb, g_opt, losses, total)

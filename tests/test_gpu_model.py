@@ -58,7 +58,7 @@ def _run_b200(g, model, render_all_heads=True, bins=None):
 @pytest.mark.parametrize("tag", ["late", "early"])
 @pytest.mark.parametrize("all_heads", [True, False])
 @pytest.mark.parametrize("own_sampler", [False, True])
-def test_train_step_matches_reference(tag, all_heads, own_sampler):
+def test_train_step_matches_reference(tag, all_heads, own_sampler, mlp_precision):
     """own_sampler=False: the sample bins come from the oracle's sampler (bit-exact to the reference) so that
     everything downstream is compared at identical sample positions — tight bands.
     own_sampler=True: the CUDA sampler runs too; its bins move by ~1e-5 (sigmoid(512 * sdf) + inverse cdf), which
@@ -68,9 +68,10 @@ def test_train_step_matches_reference(tag, all_heads, own_sampler):
     model = build_model("grid_raw", log2_hashmap_size=int(g["log2_hashmap_size"]), seed=int(g["seed"])).to(DEV)
     bins = None if own_sampler else _oracle_bins(g, model)
     outputs, losses, total = _run_b200(g, model, all_heads, bins)
-    k_ = 20.0 if own_sampler else 1.0
+    band = 3.0 if mlp_precision else 1.0        # see conftest.mlp_precision
+    k_ = (20.0 if own_sampler else 1.0) * band
     delta_t = float(g["delta"]) / (3 ** 0.5)
-    sdf_ulp = 1e-6          # the sdf (|sdf| ~ 1) is reproduced to a few fp32 ulps
+    sdf_ulp = 1e-6 * band   # the sdf (|sdf| ~ 1) is reproduced to a few fp32 ulps
     for mod in MODS:
         hit = g.t(mod + "_hit")
         heads = list(MODS) if all_heads else [mod]
@@ -97,13 +98,14 @@ def test_train_step_matches_reference(tag, all_heads, own_sampler):
             gr = sd[k[5:]].grad
             gr = gr if gr is not None else torch.zeros_like(sd[k[5:]])
             # ReLU kinks: a pre-activation within an ulp of zero flips relu' for one of ~1e3 samples of a unit
-            assert_close(gr, g.t(k), rtol=max(5e-3, 1e-3 * k_), atol=1e-7, what=k)
+            assert_close(gr, g.t(k), rtol=max(5e-3 * band, 1e-3 * k_), atol=1e-7, what=k)
         elif k.startswith("gradnorm."):
-            assert_close(sd[k[9:]].grad.norm(), g.t(k), rtol=max(5e-3, 1e-3 * k_), what=k)
+            assert_close(sd[k[9:]].grad.norm(), g.t(k), rtol=max(5e-3 * band, 1e-3 * k_), what=k)
 
 
-def test_eval_mode_is_deterministic_and_matches_oracle():
+def test_eval_mode_is_deterministic_and_matches_oracle(mlp_precision):
     from multimodalstudio_b200.cameras import RayBundle
+    band = 3.0 if mlp_precision else 1.0
     from multimodalstudio_b200.models import build_model
     model = build_model("grid_raw", log2_hashmap_size=12, seed=7).to(DEV)
     model.set_schedule_state(8, 2.0 / 64, 0.5)
@@ -124,7 +126,7 @@ def test_eval_mode_is_deterministic_and_matches_oracle():
     with torch.no_grad():
         ref = orc.forward_modality("rgb", o, d, up, None)
     for k in list(MODS) + ["normals", "accumulation", "depth"]:
-        assert_close(out[k], ref[k], rtol=3e-5, atol=1e-6, what=k)
+        assert_close(out[k], ref[k], rtol=3e-5 * band, atol=1e-6, what=k)
 
 
 def test_pose_gradients_match_oracle():
@@ -158,3 +160,40 @@ def test_pose_gradients_match_oracle():
     (((ref["mono"] - target.cpu()) ** 2).mean()).backward()
     assert_close(out["mono"], ref["mono"], rtol=3e-5, atol=1e-6, what="colour")
     assert_close(got, pa.grad, rtol=5e-3, atol=1e-7, what="d loss / d pose_adjustment")
+
+
+def test_graphed_step_equals_eager_step():
+    """RawPipeline.train_step_graphed (two CUDA graphs per step) against train_step (eager launches): same losses
+    and the same parameters after a few optimiser steps.  Stratified jitter is switched off so that neither path
+    draws random numbers (a captured torch.rand uses graph-private philox offsets)."""
+    from multimodalstudio_b200.model_components import Sampler
+    from multimodalstudio_b200.pipelines import RawPipeline, SyntheticScene
+    mods = {"rgb": 3, "polarization": 4, "multispectral": 9}
+    rays = {"rgb": 301, "polarization": 300, "multispectral": 299}
+    scene = SyntheticScene(mods, rays, seed=11)
+    batches = [scene.sample_batch() for _ in range(5)]
+    results = []
+    for graphed in (False, True):
+        pipe = RawPipeline(mods, scene.cameras, device=DEV, raw=True, log2_hashmap_size=14, seed=3)
+        for m in pipe.model.modules():
+            if isinstance(m, Sampler):
+                m.train_stratified = False
+                m.config.train_stratified = False
+        totals = []
+        for i, (cs, ts) in enumerate(batches):
+            cs = {m: c.to(DEV) for m, c in cs.items()}
+            ts = {m: t.to(DEV) for m, t in ts.items()}
+            fn = pipe.train_step_graphed if graphed else pipe.train_step
+            _, total = fn(60000 + i, cs, ts)
+            totals.append(float(total.item()))
+        if graphed:
+            assert pipe._graph is not None and pipe.graph_launches > 100
+        results.append((totals, pipe.optimizers["fields"].flat.clone(), pipe.optimizers["camera_poses"].flat.clone()))
+    (t0, p0, c0), (t1, p1, c1) = results
+    for a, b in zip(t0, t1):
+        assert abs(a - b) <= 2e-5 * abs(a), (t0, t1)
+    # Adam's first steps move every parameter by ~lr regardless of the gradient's size, so atomics-order noise in a
+    # tiny gradient can flip a step: compare against the step size
+    assert float((p0 - p1).abs().max()) <= 5e-3, float((p0 - p1).abs().max())
+    assert float((p0 - p1).abs().mean()) <= 2e-5
+    assert float((c0 - c1).abs().max()) <= 5e-4
