@@ -43,6 +43,17 @@ class RaySamples:
     def shape(self):
         return self.deltas.shape[:-1]
 
+    def slice_rays(self, a: int, b: int) -> "RaySamples":
+        """Rays [a, b) of the batch (views)."""
+        def sl(t):
+            return t[a:b] if t is not None else None
+        f = self.frustums
+        return RaySamples(
+            frustums=Frustums(origins=sl(f.origins), directions=sl(f.directions), starts=sl(f.starts), ends=sl(f.ends),
+                              pixel_area=sl(f.pixel_area), up_directions=sl(f.up_directions)),
+            camera_indices=sl(self.camera_indices), deltas=sl(self.deltas), spacing_starts=sl(self.spacing_starts),
+            spacing_ends=sl(self.spacing_ends), spacing_to_euclidean_fn=None)
+
     def get_weights_from_densities(self, densities):
         """alphas (rays.py:138-151) followed by get_weights_from_alphas (rays.py:201-217), fused."""
         return ops.DensityWeightsFn.apply(densities[..., 0], self.deltas[..., 0])[..., None]

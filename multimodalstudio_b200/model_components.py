@@ -471,8 +471,11 @@ class RadianceModel(nn.Module):
                 input_dim=self.config.radiance_feature_dim, output_dim=self.modalities[mod])
             for mod in self.modalities})
 
-    def forward(self, ray_samples: RaySamples, normals, geo_feature, heads: Optional[List[str]] = None):
-        """`heads`: subset of modality heads to evaluate (default: all, like the reference)."""
+    def forward(self, ray_samples: RaySamples, normals, geo_feature, heads=None, bounds=None):
+        """`heads`: subset of modality heads to evaluate (default: all, like the reference).
+        `bounds` ({mod: (first ray, last ray + 1)}): the batch holds the rays of several modalities; the trunk runs
+        once over all rows, the heads over each modality's rows -> {mod: {head: [R_mod, S, C]}}; `heads` is then
+        a dict {mod: [heads...]} or None (all heads for every modality)."""
         shape = ray_samples.shape
         position_input = ray_samples.frustums.get_start_positions().reshape(-1, 3)
         directions = ray_samples.frustums.directions.expand(*shape, 3).reshape(-1, 3)
@@ -496,6 +499,16 @@ class RadianceModel(nn.Module):
                                                additional_inputs=additional_input)
         outputs = {}
         up_directions = ray_samples.frustums.up_directions.expand(*shape, 3).reshape(-1, 3)
+        if bounds is not None:
+            s_ = shape[-1]
+            for mod, (a, b) in bounds.items():
+                rows = slice(a * s_, b * s_)
+                outputs[mod] = {}
+                for head in (heads[mod] if heads is not None else self.modalities):
+                    out = self.modality_heads[head](radiance_feature[rows], directions=directions[rows],
+                                                    up_directions=up_directions[rows])
+                    outputs[mod][head] = out.view(b - a, s_, -1)
+            return outputs
         for mod in (heads if heads is not None else self.modalities):
             out = self.modality_heads[mod](radiance_feature, directions=directions, up_directions=up_directions)
             outputs[mod] = out.view(*shape, -1)
@@ -536,7 +549,8 @@ class BackgroundModel(nn.Module):
                 input_dim=self.config.radiance_feature_dim, output_dim=self.modalities[mod])
             for mod in self.modalities})
 
-    def forward(self, ray_samples: RaySamples, heads: Optional[List[str]] = None):
+    def forward(self, ray_samples: RaySamples, heads=None, bounds=None):
+        """`bounds` / dict `heads`: see RadianceModel.forward -> {mod: {head: [R_mod, C]}}."""
         shape = ray_samples.shape
         inputs = ray_samples.frustums.get_start_positions().reshape(-1, 3)
         directions = ray_samples.frustums.directions.expand(*shape, 3).reshape(-1, 3)
@@ -547,6 +561,16 @@ class BackgroundModel(nn.Module):
         weights = ray_samples.get_weights_from_densities(density)
         outputs = {}
         up_directions = ray_samples.frustums.up_directions.expand(*shape, 3).reshape(-1, 3)
+        if bounds is not None:
+            s_ = shape[-1]
+            for mod, (a, b) in bounds.items():
+                rows = slice(a * s_, b * s_)
+                outputs[mod] = {}
+                for head in (heads[mod] if heads is not None else self.modalities):
+                    radiance = self.modality_heads[head](radiance_feature[rows], directions=directions[rows],
+                                                         up_directions=up_directions[rows])
+                    outputs[mod][head] = ops.CompositeFn.apply(weights[a:b, :, 0], radiance.view(b - a, s_, -1), None)
+            return outputs
         for mod in (heads if heads is not None else self.modalities):
             radiance = self.modality_heads[mod](radiance_feature, directions=directions, up_directions=up_directions)
             outputs[mod] = ops.CompositeFn.apply(weights[..., 0], radiance.view(*shape, -1), None)

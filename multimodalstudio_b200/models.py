@@ -7,6 +7,7 @@ from typing import Dict, List, Optional, Type
 
 import torch
 
+from .cameras import RayBundle
 from .configs import InstantiateConfig, update_config
 from .field_components import (FeatureGridAndMLPConfig, FeatureGridConfig, HashEncodingConfig, MLPConfig,
                                ModalityHeadConfig, NeRFEncodingConfig, PolarizationHeadConfig, SceneContractionConfig,
@@ -43,6 +44,12 @@ class BaseModelConfig(InstantiateConfig):
     """True: every modality's rays go through all M heads like the reference (radiance_model.py:143-149).
     False: only the head of the bundle's own modality is evaluated — the only one the losses read
     (losses.py:225); identical loss and gradients."""
+    batch_modalities: bool = True
+    """True: the rays of all modalities run through the shared networks (sampler's SDF queries, SDF field + taps,
+    radiance trunk, background field) as ONE batch; only the modality heads, the compositing and the losses see
+    per-modality row ranges.  Every operator is row-independent, so the outputs equal those of the reference's
+    per-modality loop (base_model.py:102-159) up to the summation order of the parameter gradients.
+    False: the reference's loop."""
 
 
 class BaseModel(torch.nn.Module):
@@ -65,6 +72,8 @@ class BaseModel(torch.nn.Module):
 
     def forward(self, ray_bundles, rand: Optional[dict] = None):
         rand = rand or {}
+        if self.config.batch_modalities and sum(rb is not None for rb in ray_bundles.values()) > 1:
+            return self._forward_batched(ray_bundles, rand)
         masks = self.collider.update_ray_bundles(ray_bundles)
         sampler_out = self.ray_sampler(ray_bundles, sdf_fn=self.surface_model.get_sdf, rand=rand)
         samples_per_modality = sampler_out["ray_samples_per_modality"]
@@ -94,6 +103,62 @@ class BaseModel(torch.nn.Module):
                 modality_outputs.update({"gradients": geometry["gradients"], "hessians": geometry["hessians"],
                                          "inv_s": geometry["inv_s"], "ray_mask": mask})
             outputs[mod] = modality_outputs
+        return outputs
+
+    def _forward_batched(self, ray_bundles, rand):
+        """All modalities as one ray batch through the shared networks (see BaseModelConfig.batch_modalities)."""
+        ALL = "__all__"
+        mods = [m for m, rb in ray_bundles.items() if rb is not None]
+        bundles = [ray_bundles[m] for m in mods]
+        counts = [len(rb) for rb in bundles]
+        bounds, off = {}, 0
+        for m, c in zip(mods, counts):
+            bounds[m] = (off, off + c)
+            off += c
+
+        def cat_attr(name):
+            vals = [getattr(rb, name) for rb in bundles]
+            return torch.cat(vals, 0) if all(v is not None for v in vals) else None
+
+        big = RayBundle(camera_indices=cat_attr("camera_indices"), origins=cat_attr("origins"),
+                        directions=cat_attr("directions"), up_directions=cat_attr("up_directions"),
+                        pixel_area=cat_attr("pixel_area"), directions_norm=cat_attr("directions_norm"))
+
+        def cat_rand(key):
+            d = rand.get(key)
+            if not d or all(d.get(m) is None for m in mods):
+                return None
+            if any(d.get(m) is None for m in mods):
+                raise ValueError(f"rand['{key}'] must be given for every modality or for none")
+            if isinstance(d[mods[0]], (list, tuple)):
+                return {ALL: [torch.cat([d[m][i] for m in mods], 0) for i in range(len(d[mods[0]]))]}
+            return {ALL: torch.cat([d[m] for m in mods], 0)}
+
+        rand_all = {k: cat_rand(k) for k in ("uniform", "pdf", "bins")}
+        mask = self.collider.update_ray_bundles({ALL: big})[ALL]
+        samples = self.ray_sampler({ALL: big}, sdf_fn=self.surface_model.get_sdf, rand=rand_all)["ray_samples_per_modality"][ALL]
+        background = None
+        if self.config.use_background_model:
+            self.collider.update_ray_bundles_for_background({ALL: big})
+            bg_samples = self.background_ray_sampler({ALL: big}, rand=cat_rand("background"))[ALL]
+            heads = None if self.config.render_all_heads else {m: [m] for m in mods}
+            background = self.background_model(bg_samples, heads=heads, bounds=bounds)
+        geometry = self.surface_model(samples, mask=mask)
+        heads = None if self.config.render_all_heads else {m: [m] for m in mods}
+        radiance = self.radiance_model(ray_samples=samples, normals=geometry["normals"].detach(),
+                                       geo_feature=geometry["geo_feature"], heads=heads, bounds=bounds)
+        outputs = {m: None for m in ray_bundles}
+        for m in mods:
+            a, b = bounds[m]
+            renderer_input = dict(radiance[m])
+            renderer_input.update({"normals": geometry["normals"][a:b], "depth": samples.slice_rays(a, b),
+                                   "background": background[m] if background is not None else None})
+            out = self.renderer.render(geometry["weights"][a:b], renderer_input, mask[a:b] if mask is not None else None)
+            if self.training:
+                out.update({"gradients": geometry["gradients"][a:b],
+                            "hessians": geometry["hessians"][a:b] if geometry["hessians"] is not None else None,
+                            "inv_s": geometry["inv_s"], "ray_mask": mask[a:b] if mask is not None else None})
+            outputs[m] = out
         return outputs
 
     def get_param_groups(self):
@@ -210,7 +275,8 @@ GRID_YAML_MODEL = {
 def build_model(preset: str = "grid_raw", modalities: Optional[Dict[str, int]] = None, yaml_model: Optional[dict] = None,
                 interpolation: str = "Linear", direction_encoding: str = "nerf", log2_hashmap_size: Optional[int] = None,
                 num_samples: Optional[int] = None, num_samples_importance: Optional[int] = None,
-                bg_samples: Optional[int] = None, render_all_heads: bool = True, seed: Optional[int] = 654824):
+                bg_samples: Optional[int] = None, render_all_heads: bool = True, seed: Optional[int] = 654824,
+                batch_modalities: bool = True):
     """Builds the BaseModel of a preset after the YAML overrides, with the tcnn-free substitutions the
     pinned oracle uses (Linear interpolation, NeRF direction encoding).  Construction order and
     RNG consumption match the reference, so the same torch seed gives the same initial parameters."""
@@ -238,6 +304,7 @@ def build_model(preset: str = "grid_raw", modalities: Optional[Dict[str, int]] =
     if bg_samples is not None:
         cfg.background_ray_sampler.num_samples = bg_samples
     cfg.render_all_heads = render_all_heads
+    cfg.batch_modalities = batch_modalities
     if modalities is None:
         modalities = dict(MODALITY_CHANNELS)
     if seed is not None:

@@ -197,3 +197,26 @@ def test_graphed_step_equals_eager_step():
     assert float((p0 - p1).abs().max()) <= 5e-3, float((p0 - p1).abs().max())
     assert float((p0 - p1).abs().mean()) <= 2e-5
     assert float((c0 - c1).abs().max()) <= 5e-4
+
+
+@pytest.mark.parametrize("all_heads", [True, False])
+def test_batched_modalities_equal_the_per_modality_loop(all_heads):
+    """BaseModelConfig.batch_modalities: one ray batch through the shared networks against the reference's
+    per-modality loop, on the reference's own inputs (fixture model_late): same outputs, same gradients."""
+    from multimodalstudio_b200.models import build_model
+    g = load_golden("model_late")
+    res = []
+    for batched in (False, True):
+        model = build_model("grid_raw", log2_hashmap_size=int(g["log2_hashmap_size"]), seed=int(g["seed"]),
+                            batch_modalities=batched).to(DEV)
+        outputs, losses, total = _run_b200(g, model, all_heads, _oracle_bins(g, model))
+        total.backward()
+        res.append((outputs, total, {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}))
+    (o0, t0, g0), (o1, t1, g1) = res
+    for mod in MODS:
+        for k in (list(MODS) if all_heads else [mod]) + ["accumulation", "depth", "normals", "gradients", "hessians"]:
+            assert_close(o1[mod][k], o0[mod][k], rtol=1e-6, atol=1e-7, what=f"{mod} {k}")
+    assert_close(t1, t0, rtol=1e-6, what="total loss")
+    assert set(g0) == set(g1)
+    for k in g0:
+        assert_close(g1[k], g0[k], rtol=2e-3, atol=1e-8, what=k)     # summation order of the weight gradients (split-K atomics)
