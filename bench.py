@@ -163,7 +163,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     mods = {m: MODALITY_CHANNELS[m] for m in wl["modalities"]}
     rays = split_rays(wl["rays"], wl["modalities"])
     scene = SyntheticScene(mods, rays, raw=wl["raw"], seed=654824 + rank)      # pixel_samplers.py:49-52 rank-offset seed
@@ -243,10 +244,11 @@ def main():
     roof, roof_hash = None, None
     if rank == 0:
         _lib.start_kernel_timing(None)
-        for i in range(2):
-            cs, ts = resident[i % n_batches]
-            pipe.train_step(BASE_STEP + i, cs, ts)          # eager: events cannot be recorded inside a graph replay
-        torch.cuda.synchronize()
+    for i in range(2):                                      # every rank steps (the gradient all-reduce is collective)
+        cs, ts = resident[i % n_batches]
+        pipe.train_step(BASE_STEP + i, cs, ts)              # eager: events cannot be recorded inside a graph replay
+    torch.cuda.synchronize()
+    if rank == 0:
         rec = _lib.stop_kernel_timing()
         flops = {"mmsb_linear_fwd": 0.0, "mmsb_linear_bwd_data": 0.0, "mmsb_linear_bwd_weight": 0.0}
         msk = {k: 0.0 for k in flops}

@@ -421,35 +421,44 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g) {
     }
   } else if (warp < EPI_WARPS + PROD_WARPS) {
     // ================= producers: A (global fp32) -> hi/lo -> swizzled shared memory =================
+    // A ring of LOOKAHEAD register buffers keeps the global loads of the next k-blocks in flight while the current
+    // one is split and stored: one k-block of MMAs (~0.8 us) is shorter than a loaded HBM round trip.
+    constexpr int LOOKAHEAD = 3;
     const int p = t - EPI_WARPS * 32;
     const int c = p & 7, r_base = p >> 3;
     const bool vec = ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
-    float4 v[4];
-    int64_t tile = blockIdx.x;
-    int kb = 0;
-    if (tile < g.total_tiles) {
-      const int64_t m0 = (tile / g.n_tiles) * TM;
+    float4 v[LOOKAHEAD][4];
+    int64_t tile_l = blockIdx.x;   // load cursor (runs LOOKAHEAD k-blocks ahead of the store cursor)
+    int kb_l = 0;
+    auto load_next = [&](float4 (&dst)[4]) {
+      if (tile_l < g.total_tiles) {
+        const int64_t m0 = (tile_l / g.n_tiles) * TM;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = load4(g.A, g.lda, m0 + r_base + 32 * i, g.M, c * 4, g.K, vec);
-    }
-    uint32_t it = 0;
-    while (tile < g.total_tiles) {
-      const uint32_t s = it % S;
-      mbar_wait(bar_empty + 8 * s, ((it / S) & 1) ^ 1);
-      uint8_t* a_hi = smem + s * STAGE;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = r_base + 32 * i;
-        split_store4<NPARTS>(a_hi, a_hi + PART, uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4), v[i]);
+        for (int i = 0; i < 4; ++i) dst[i] = load4(g.A, g.lda, m0 + r_base + 32 * i, g.M, kb_l * TK + c * 4, g.K, vec);
+        if (++kb_l == g.nkb) { kb_l = 0; tile_l += gridDim.x; }
       }
-      fence_async_smem();
-      mbar_arrive(bar_full + 8 * s);
-      ++it;
-      if (++kb == g.nkb) { kb = 0; tile += gridDim.x; }
-      if (tile < g.total_tiles) {
-        const int64_t m0 = (tile / g.n_tiles) * TM;
+    };
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = load4(g.A, g.lda, m0 + r_base + 32 * i, g.M, kb * TK + c * 4, g.K, vec);
+    for (int d = 0; d < LOOKAHEAD; ++d) load_next(v[d]);
+    const int64_t my_tiles = blockIdx.x < g.total_tiles ? (g.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t iters = my_tiles * g.nkb;
+    for (int64_t it0 = 0; it0 < iters; it0 += LOOKAHEAD) {
+#pragma unroll
+      for (int d = 0; d < LOOKAHEAD; ++d) {
+        const int64_t it = it0 + d;
+        if (it < iters) {
+          const uint32_t s = uint32_t(it % S);
+          mbar_wait(bar_empty + 8 * s, (uint32_t(it / S) & 1) ^ 1);
+          uint8_t* a_hi = smem + s * STAGE;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = r_base + 32 * i;
+            split_store4<NPARTS>(a_hi, a_hi + PART, uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4), v[d][i]);
+          }
+          fence_async_smem();
+          mbar_arrive(bar_full + 8 * s);
+          load_next(v[d]);
+        }
       }
     }
   } else if (warp == EPI_WARPS + PROD_WARPS) {
@@ -545,7 +554,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const WgradArgs g)
 
   if (t == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(bar_full + 8 * s, PROD_THREADS);
+      mbar_init(bar_full + 8 * s, (EPI_WARPS + PROD_WARPS) * 32);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_tfull, 1);
@@ -562,65 +571,78 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const WgradArgs g)
   const uint32_t tmem = *tmem_slot;
 
   if (nkb > 0) {
-    if (warp < EPI_WARPS) {
-      // ================= epilogue: partial tile -> dW with coalesced reductions =================
-      float* stg = stg_all + warp * 32 * STG_LD;
-      EpiArgs e{};
-      e.C = g.dw; e.ldc = g.lddw; e.M = g.out_dim; e.N = g.in_dim;
-      mbar_wait(bar_tfull, 0);
-      tc_fence_after();
-      YPrev y_none;
-      epilogue_tile<EPI_ATOMIC>(e, tmem, w, stg, warp, lane, m0, n0, false, false, y_none, []() {});
-    } else if (warp < EPI_WARPS + PROD_WARPS) {
+    if (warp < EPI_WARPS + PROD_WARPS) {
       // ================= producers: dz and x rows -> hi/lo -> MN-major swizzled shared memory =================
-      const int p = t - EPI_WARPS * 32;
-      const int ca = p & 31, ka = p >> 5;     // dz tile: 32 chunks per row, rows ka + 8 i
-      const int cb = p & 63, kbb = p >> 6;    // x tile : up to 64 chunks per row, rows kbb + 4 i
+      // all 16 non-issuing warps stage operands during the mainloop (the 8 epilogue warps have nothing else to do
+      // until the accumulator is complete); LOOKAHEAD register buffers keep the next k-blocks' loads in flight
+      constexpr int LOOKAHEAD = 2;
+      constexpr int NPROD = (EPI_WARPS + PROD_WARPS) * 32;   // 512
+      const int ca = t & 31, ka = t >> 5;      // dz tile: 32 chunks per k-row, k-rows ka + 16 i (i < 2)
+      const int cb = t & 63, kbb = t >> 6;     // x tile : up to 64 chunks per k-row, k-rows kbb + 8 i (i < 4)
+      static_assert(NPROD == 512, "producer mapping assumes 512 threads");
       const bool vec_a = ((g.lddz & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.dz) & 15) == 0);
       const bool vec_b = ((g.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.x) & 15) == 0);
       const bool b_active = cb < cpr;
       const bool want_db = g.db != nullptr && nt == 0;
       float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 va[4], vb[8];
-      auto load_block = [&](int kb) {
+      float4 va[LOOKAHEAD][2], vb[LOOKAHEAD][4];
+      auto load_block = [&](int kb, float4 (&a)[2], float4 (&b)[4]) {
+        if (kb >= nkb) return;
         const int64_t k0 = k_beg + int64_t(kb) * TK;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) va[i] = load4(g.dz, g.lddz, k0 + ka + 8 * i, k_end, m0 + ca * 4, g.out_dim, vec_a);
+        for (int i = 0; i < 2; ++i) a[i] = load4(g.dz, g.lddz, k0 + ka + 16 * i, k_end, m0 + ca * 4, g.out_dim, vec_a);
         if (b_active) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) vb[i] = load4(g.x, g.ldx, k0 + kbb + 4 * i, k_end, n0 + cb * 4, g.in_dim, vec_b);
+          for (int i = 0; i < 4; ++i) b[i] = load4(g.x, g.ldx, k0 + kbb + 8 * i, k_end, n0 + cb * 4, g.in_dim, vec_b);
         }
       };
-      load_block(0);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const uint32_t s = kb % S;
-        mbar_wait(bar_empty + 8 * s, ((kb / S) & 1) ^ 1);
-        uint8_t* a_hi = smem + s * STAGE;
-        uint8_t* b_hi = a_hi + NPARTS * PART;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int k = ka + 8 * i;
-          split_store4<NPARTS>(a_hi, a_hi + PART, mn_offset(ca, k), va[i]);
-          colsum.x += va[i].x; colsum.y += va[i].y; colsum.z += va[i].z; colsum.w += va[i].w;
-        }
-        if (b_active) {
+      for (int d = 0; d < LOOKAHEAD; ++d) load_block(d, va[d], vb[d]);
+      for (int kb0 = 0; kb0 < nkb; kb0 += LOOKAHEAD) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int k = kbb + 4 * i;
-            split_store4<NPARTS>(b_hi, b_hi + b_part, mn_offset(cb, k), vb[i]);
+        for (int d = 0; d < LOOKAHEAD; ++d) {
+          const int kb = kb0 + d;
+          if (kb < nkb) {
+            const uint32_t s = kb % S;
+            mbar_wait(bar_empty + 8 * s, ((kb / S) & 1) ^ 1);
+            uint8_t* a_hi = smem + s * STAGE;
+            uint8_t* b_hi = a_hi + NPARTS * PART;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int k = ka + 16 * i;
+              split_store4<NPARTS>(a_hi, a_hi + PART, mn_offset(ca, k), va[d][i]);
+              colsum.x += va[d][i].x; colsum.y += va[d][i].y; colsum.z += va[d][i].z; colsum.w += va[d][i].w;
+            }
+            if (b_active) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int k = kbb + 8 * i;
+                split_store4<NPARTS>(b_hi, b_hi + b_part, mn_offset(cb, k), vb[d][i]);
+              }
+            }
+            fence_async_smem();
+            mbar_arrive(bar_full + 8 * s);
+            load_block(kb + LOOKAHEAD, va[d], vb[d]);
           }
         }
-        fence_async_smem();
-        mbar_arrive(bar_full + 8 * s);
-        if (kb + 1 < nkb) load_block(kb + 1);
       }
       if (want_db) {
-        // the 8 producer warps hold partial column sums for the same 128 columns: combine through the L2
+        // 16 warps hold partial column sums for the same 128 columns: combine through the L2
         const int col = m0 + ca * 4;
         if (col < g.out_dim) atomicAdd(g.db + col, colsum.x);
         if (col + 1 < g.out_dim) atomicAdd(g.db + col + 1, colsum.y);
         if (col + 2 < g.out_dim) atomicAdd(g.db + col + 2, colsum.z);
         if (col + 3 < g.out_dim) atomicAdd(g.db + col + 3, colsum.w);
+      }
+      if (warp < EPI_WARPS) {
+        // ================= epilogue: partial tile -> dW with coalesced reductions =================
+        float* stg = stg_all + warp * 32 * STG_LD;
+        EpiArgs e{};
+        e.C = g.dw; e.ldc = g.lddw; e.M = g.out_dim; e.N = g.in_dim;
+        mbar_wait(bar_tfull, 0);
+        tc_fence_after();
+        YPrev y_none;
+        epilogue_tile<EPI_ATOMIC>(e, tmem, w, stg, warp, lane, m0, n0, false, false, y_none, []() {});
       }
     } else if (warp == EPI_WARPS + PROD_WARPS + 1) {
       // ================= MMA issuer =================

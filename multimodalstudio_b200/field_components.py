@@ -118,6 +118,10 @@ class NeRFEncoding(Encoding):
     def forward(self, input_tensor):
         return ops.NerfEncodingFn.apply(input_tensor, self.freqs, self.include_input)
 
+    def piece(self, input_tensor):
+        """This encoding as a column range of an `ops.assemble` row (written in place by the kernel)."""
+        return ops.nerf_piece(input_tensor.reshape(-1, input_tensor.shape[-1]), self.freqs, self.include_input)
+
 
 class HashEncoding(Encoding):
     """ref: encodings.py:184-310 (torch path semantics; table layout [L * 2^log2, F] fp32)."""
@@ -170,6 +174,9 @@ class SHEncoding(Encoding):
 
     def forward(self, input_tensor):
         return ops.SHEncodingFn.apply(input_tensor, self.config.degree + 1)
+
+    def piece(self, input_tensor):
+        return ops.copy_piece(self.forward(input_tensor.reshape(-1, 3)))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -309,6 +316,10 @@ class FeatureGrid(FieldComponent):
     def forward(self, input_tensor):
         return self.encoding(input_tensor, radius=float(self.radius), mask=self._mask_on(input_tensor.device))
 
+    def piece(self, positions):
+        return ops.hash_piece(positions.reshape(-1, 3), self.encoding.hash_table, self._mask_on(positions.device),
+                              self.encoding.desc(float(self.radius)))
+
     def update_mask(self, level: int):
         self.active_level = int(level)
         self.hash_encoding_mask[:] = 1.0
@@ -351,7 +362,14 @@ class FeatureGridAndMLP(FieldComponent):
         self.mlp_head = self.config.mlp_head.setup(input_dim=mlp_input_dim, output_dim=output_dim)
         self.output_dim = self.mlp_head.get_out_dim()
 
-    def forward(self, input_tensor, n_out_used: Optional[int] = None):
+    def forward(self, input_tensor=None, n_out_used: Optional[int] = None, pieces=None, positions=None):
+        """`pieces` + `positions`: the row cat[pieces..., hash features(positions)] is assembled in place by the
+        encoder kernels (ops.assemble) instead of torch.cat over materialised parts — same values."""
+        if pieces is not None and not self.config.return_features:
+            mlp_input = ops.assemble(list(pieces) + [self.feature_grid.piece(positions)])
+            return self.mlp_head(mlp_input, n_out_used=n_out_used)
+        if input_tensor is None:
+            input_tensor = ops.assemble(list(pieces))
         features = self.feature_grid(input_tensor[..., :3])
         mlp_input = torch.cat([input_tensor, features], dim=-1)   # == cat[x, aux, features]
         output = self.mlp_head(mlp_input, n_out_used=n_out_used)

@@ -6,6 +6,7 @@ from typing import Optional, Type
 
 import torch
 
+from . import ops
 from .configs import InstantiateConfig
 from .field_components import (EncodingConfig, FieldComponent, FieldComponentConfig, MLPConfig, ModalityHeadConfig,
                                NeRFEncodingConfig)
@@ -53,11 +54,18 @@ class SDFField(SurfaceField):
         self.field = self.config.field.setup(input_dim=self.input_dim, output_dim=self.output_dim)
 
     def forward(self, x, sdf_only: bool = False):
-        if self.config.use_position_encoding:
-            x = self.position_encoding(x)
-        if sdf_only:
-            return self.field(x, n_out_used=1), None
-        out = self.field(x)
+        if self.config.use_position_encoding and hasattr(self.field, "feature_grid"):
+            # cat[PE(x), hash(x)] written in place by the two encoders
+            kw = dict(pieces=[self.position_encoding.piece(x)], positions=x)
+            if sdf_only:
+                return self.field(n_out_used=1, **kw), None
+            out = self.field(**kw)
+        else:
+            if self.config.use_position_encoding:
+                x = self.position_encoding(x)
+            if sdf_only:
+                return self.field(x, n_out_used=1), None
+            out = self.field(x)
         if self.config.geo_feature_dim is not None:
             sdf, geo_feature = torch.split(out, [1, self.config.geo_feature_dim], dim=-1)
         else:
@@ -85,7 +93,17 @@ class RadianceField(FieldComponent):
         super().__init__(config, input_dim=input_dim, output_dim=output_dim)
         self.base_field = self.config.base_field.setup(input_dim=self.input_dim, output_dim=self.output_dim)
 
-    def forward(self, positions, view_directions, additional_inputs):
+    def forward(self, positions, view_directions, additional_inputs, view_direction_piece=None):
+        if hasattr(self.base_field, "feature_grid"):
+            pieces = [ops.copy_piece(positions),
+                      view_direction_piece if view_direction_piece is not None else ops.copy_piece(view_directions)]
+            pieces += [ops.copy_piece(a) for a in (additional_inputs if isinstance(additional_inputs, (list, tuple))
+                                                   else [additional_inputs])]
+            return self.base_field(pieces=pieces, positions=positions)
+        if isinstance(additional_inputs, (list, tuple)):
+            additional_inputs = torch.cat(list(additional_inputs), dim=-1)
+        if view_directions is None:
+            view_directions = ops.assemble([view_direction_piece])
         inputs = torch.cat([positions, view_directions, additional_inputs], dim=-1)
         return self.base_field(inputs)
 
@@ -125,12 +143,11 @@ class NeRFField(torch.nn.Module):
         ).setup(input_dim=self.base_field.output_dim, output_dim=1)
 
     def forward(self, x, viewing_direction):
-        if self.config.use_position_encoding:
-            x = self.position_encoding(x)
-        if self.config.use_direction_encoding:
-            viewing_direction = self.direction_encoding(viewing_direction)
+        x = ops.assemble([self.position_encoding.piece(x) if self.config.use_position_encoding else ops.copy_piece(x)])
         feature = self.base_field(x)
         density = self.density_head(feature)
-        head_input = torch.cat([feature, viewing_direction], dim=-1)
+        head_input = ops.assemble([ops.copy_piece(feature),
+                                   self.direction_encoding.piece(viewing_direction) if self.config.use_direction_encoding
+                                   else ops.copy_piece(viewing_direction)])
         feature = self.head_field(head_input)
         return density, feature

@@ -492,11 +492,11 @@ class RadianceModel(nn.Module):
             if n_dot_v is None:
                 n_dot_v = torch.sum(normals * -directions, dim=-1, keepdim=True)
             direction_input = 2 * (n_dot_v * normals) + direction_input
+        direction_piece = None
         if self.config.use_direction_encoding:
-            direction_input = self.direction_encoding(direction_input)
-        additional_input = torch.cat(additional_input, dim=-1)
+            direction_piece, direction_input = self.direction_encoding.piece(direction_input), None
         radiance_feature = self.radiance_field(positions=position_input, view_directions=direction_input,
-                                               additional_inputs=additional_input)
+                                               additional_inputs=additional_input, view_direction_piece=direction_piece)
         outputs = {}
         up_directions = ray_samples.frustums.up_directions.expand(*shape, 3).reshape(-1, 3)
         if bounds is not None:

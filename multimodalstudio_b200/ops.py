@@ -45,10 +45,19 @@ def _f(t: torch.Tensor) -> torch.Tensor:
 
 
 def _rows(t: torch.Tensor, last: int) -> torch.Tensor:
-    """[..., last] -> contiguous [n, last]"""
+    """[..., last] -> [n, last] with unit column stride (row-strided 2-D inputs, e.g. the padded rows of
+    `assemble`, pass through without a copy: every kernel takes its leading dimension)."""
     if t.shape[-1] != last:
         raise ValueError(f"expected last dimension {last}, got {tuple(t.shape)}")
+    if t.dim() == 2 and t.is_cuda and t.dtype == torch.float32 and t.stride(1) == 1 and t.stride(0) >= last:
+        return t
     return _f(t).reshape(-1, last)
+
+
+def _padded_rows(n: int, cols: int, device) -> torch.Tensor:
+    """[n, cols] fp32 view whose rows start on 16-byte boundaries (leading dimension rounded up to 4 floats)."""
+    ld = (cols + 3) // 4 * 4
+    return torch.empty((n, ld), device=device, dtype=torch.float32)[:, :cols]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -202,6 +211,143 @@ class SHEncodingFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+# MLP input assembly: cat[x, encodings(x), features, hash features] written in place by the encoders
+# (feature_structures.py:164 / radiance_field.py:73 / nerf_field.py:101 build these rows with torch.cat)
+# ------------------------------------------------------------------------------------------------
+def copy_piece(t):
+    return ("copy", t)
+
+
+def nerf_piece(x, freqs, include_input):
+    return ("nerf", x, tuple(freqs), bool(include_input))
+
+
+def hash_piece(x, table, mask, desc):
+    return ("hash", x, table, mask, desc)
+
+
+def _piece_width(p):
+    if p[0] == "copy":
+        return p[1].shape[-1]
+    if p[0] == "nerf":
+        return nerf_out_dim(p[1].shape[-1], len(p[2]), p[3])
+    return p[4].num_levels * p[4].features_per_level
+
+
+class AssembleFn(torch.autograd.Function):
+    """rows = cat(pieces, -1), every piece written by its producer kernel straight into its column range of one
+    16-byte-aligned row buffer (no torch.cat, no second pass); backward reads the column ranges of the incoming
+    gradient in place.  spec: tuple of ("copy", i) | ("nerf", i, freqs, include_input) | ("hash", i, j, mask, desc)
+    where i / j index `tensors` (a tensor feeding several pieces appears once: its gradient is accumulated here)."""
+
+    @staticmethod
+    def forward(ctx, spec, *tensors):
+        n = tensors[spec[0][1]].reshape(-1, tensors[spec[0][1]].shape[-1]).shape[0]
+        widths = []
+        for p in spec:
+            if p[0] == "copy":
+                widths.append(tensors[p[1]].shape[-1])
+            elif p[0] == "nerf":
+                widths.append(nerf_out_dim(tensors[p[1]].shape[-1], len(p[2]), p[3]))
+            else:
+                widths.append(p[4].num_levels * p[4].features_per_level)
+        total = sum(widths)
+        dev = tensors[0].device
+        out = _padded_rows(n, total, dev)
+        saved, col = {}, 0
+        for p, w in zip(spec, widths):
+            if p[0] == "copy":
+                out[:, col:col + w].copy_(tensors[p[1]].reshape(n, w))
+            elif p[0] == "nerf":
+                x2 = saved.setdefault(p[1], _rows(tensors[p[1]], tensors[p[1]].shape[-1]))
+                nerf_fwd_into(x2, list(p[2]), p[3], out, col)
+            else:
+                x2 = saved.setdefault(p[1], _rows(tensors[p[1]], 3))
+                tab = saved.setdefault(p[2], _f(tensors[p[2]]))
+                hashgrid_fwd_into(p[4], x2, tab, p[3], out, col)
+            col += w
+        keys = sorted(saved)
+        ctx.save_for_backward(*[saved[k] for k in keys])
+        ctx.keys, ctx.spec, ctx.widths = keys, spec, widths
+        ctx.shapes = [t.shape for t in tensors]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        saved = dict(zip(ctx.keys, ctx.saved_tensors))
+        spec, widths = ctx.spec, ctx.widths
+        n, total = dout.shape
+        if not (dout.stride(1) == 1 and dout.dtype == torch.float32):
+            dout = dout.contiguous().float()
+        grads = [None] * len(ctx.shapes)
+        written = set()
+        cols, col = [], 0
+        for w in widths:
+            cols.append(col)
+            col += w
+        # hash pieces first (the kernel writes dx), then the nerf pieces accumulate into the same dx
+        order = sorted(range(len(spec)), key=lambda i: {"hash": 0, "nerf": 1, "copy": 2}[spec[i][0]])
+        for i in order:
+            p, w, c = spec[i], widths[i], cols[i]
+            if p[0] == "copy":
+                if ctx.needs_input_grad[1 + p[1]]:
+                    g = dout[:, c:c + w].reshape(ctx.shapes[p[1]]) if dout[:, c:c + w].is_contiguous() else dout[:, c:c + w]
+                    g = g if g.shape == ctx.shapes[p[1]] else g.reshape(ctx.shapes[p[1]])
+                    grads[p[1]] = g if grads[p[1]] is None else grads[p[1]] + g
+            elif p[0] == "hash":
+                x2, tab = saved[p[1]], saved[p[2]]
+                need_x, need_t = ctx.needs_input_grad[1 + p[1]], ctx.needs_input_grad[1 + p[2]]
+                if not (need_x or need_t):
+                    continue
+                dtable = torch.zeros_like(tab) if need_t else None
+                dx = None
+                if need_x:
+                    if p[1] in written:
+                        raise NotImplementedError("two hash pieces on one input")
+                    dx = torch.empty((n, 3), device=dout.device, dtype=torch.float32)
+                    written.add(p[1])
+                    grads[p[1]] = dx
+                hashgrid_bwd_from(p[4], x2, tab, p[3], dout, c, dtable, dx)
+                if need_t:
+                    grads[p[2]] = dtable if grads[p[2]] is None else grads[p[2]] + dtable
+            else:
+                if not ctx.needs_input_grad[1 + p[1]]:
+                    continue
+                x2 = saved[p[1]]
+                if grads[p[1]] is None:
+                    grads[p[1]] = torch.empty((n, x2.shape[1]), device=dout.device, dtype=torch.float32)
+                    nerf_bwd_from(x2, list(p[2]), p[3], dout, c, grads[p[1]], False)
+                else:
+                    nerf_bwd_from(x2, list(p[2]), p[3], dout, c, grads[p[1]], True)
+        for i, g in enumerate(grads):
+            if g is not None and tuple(g.shape) != tuple(ctx.shapes[i]):
+                grads[i] = g.reshape(ctx.shapes[i])
+        return (None, *grads)
+
+
+def assemble(pieces):
+    """pieces: list from copy_piece / nerf_piece / hash_piece -> row-strided [n, sum(widths)] tensor."""
+    tensors, index = [], {}
+
+    def idx(t):
+        k = id(t)
+        if k not in index:
+            index[k] = len(tensors)
+            tensors.append(t)
+        return index[k]
+
+    spec = []
+    for p in pieces:
+        if p[0] == "copy":
+            spec.append(("copy", idx(p[1])))
+        elif p[0] == "nerf":
+            spec.append(("nerf", idx(p[1]), p[2], p[3]))
+        else:
+            spec.append(("hash", idx(p[1]), idx(p[2]), p[3], p[4]))
+    return AssembleFn.apply(tuple(spec), *tensors)
+
+
+# ------------------------------------------------------------------------------------------------
 # MLP (A11)
 # ------------------------------------------------------------------------------------------------
 def linear_fwd(x, w, b, act, act_param, out=None):
@@ -343,12 +489,12 @@ class MLPFn(torch.autograd.Function):
         x2 = acts[0] if 0 not in skips else None
         n = acts[0].shape[0]
         out_dim = acts[nl].shape[1]
-        dz = _f(dy).reshape(n, out_dim)
+        dz = _rows(dy.reshape(n, out_dim) if dy.dim() != 2 else dy, out_dim)
         # activation derivative of the output layer
         if out_act != 0:
-            dz_new = torch.empty_like(dz)
-            call("mmsb_act_bwd", ptr(dz), _i64(out_dim), ptr(acts[nl]), _i64(out_dim), ptr(dz_new), _i64(out_dim),
-                 _i64(n), _i32(out_dim), _i32(out_act), _f32(act_param), stream_ptr())
+            dz_new = _padded_rows(n, out_dim, dz.device)
+            call("mmsb_act_bwd", ptr(dz), _i64(dz.stride(0)), ptr(acts[nl]), _i64(acts[nl].stride(0)), ptr(dz_new),
+                 _i64(dz_new.stride(0)), _i64(n), _i32(out_dim), _i32(out_act), _f32(act_param), stream_ptr())
             dz = dz_new
         grads = [None] * (2 * nl)
         dx_skip = None
@@ -378,14 +524,14 @@ class MLPFn(torch.autograd.Function):
                 grads[2 * i + 1] = db
             if i == 0 and not need_dx:
                 break
-            dxin = torch.empty((n, k), device=w.device, dtype=torch.float32)
+            dxin = _padded_rows(n, k, w.device)
             # the input of layer i is the hidden activation of layer i-1 (unless a skip concat sits between)
             fuse_prev = i > 0 and i not in skips
             if tc:
                 linear_bwd_data_tc(dz, ctx.packed_t[i], k, xin if fuse_prev else None,
                                    hidden_act if fuse_prev else 0, act_param, prec, out=dxin)
             else:
-                call("mmsb_linear_bwd_data", ptr(dz), _i64(dz.stride(0)), ptr(w), ptr(dxin), _i64(k),
+                call("mmsb_linear_bwd_data", ptr(dz), _i64(dz.stride(0)), ptr(w), ptr(dxin), _i64(dxin.stride(0)),
                      ptr(xin) if fuse_prev else None, _i64(xin.stride(0)), _i32(hidden_act if fuse_prev else 0),
                      _f32(act_param), _i64(n), _i32(k), _i32(o), stream_ptr())
             if i in skips:
