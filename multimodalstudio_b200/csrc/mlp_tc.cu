@@ -20,6 +20,7 @@
 //       SWIZZLE_128B_BASE32B tiles; the bias gradient (column sums of dz) is accumulated by the producers on the way;
 //       partial tiles are combined with coalesced fp32 reductions (red.global.add).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mmsb {
 namespace tc {
@@ -29,9 +30,11 @@ constexpr int TK = 32;             // fp32 per k-block = one 128-byte swizzle ro
 constexpr int NT = 256;            // widest accumulator (UMMA N)
 constexpr int PART = TM * 128;     // bytes of one A part (hi or lo) of a stage
 constexpr int BPART = NT * 128;    // bytes reserved for one B part of a stage
-constexpr int EPI_WARPS = 8, PROD_WARPS = 8;                 // two epilogue warps per TMEM lane quadrant
+constexpr int EPI_WARPS = 8, PROD_WARPS = 8;                 // two epilogue warps per TMEM lane quadrant; 2 producer groups
 constexpr int PROD_THREADS = PROD_WARPS * 32;
-constexpr int THREADS = (EPI_WARPS + PROD_WARPS + 2) * 32;   // + B-loader warp + MMA warp
+constexpr int THREADS = (EPI_WARPS + PROD_WARPS + 2) * 32;   // rows kernel: + B-loader warp + MMA warp
+constexpr int WG_STAGE_WARPS = 16;                           // weight-gradient kernel: 2 groups of 8 staging warps
+constexpr int WG_THREADS = (WG_STAGE_WARPS + 1) * 32;        // + MMA warp
 constexpr int CH = 16;                                       // accumulator columns per epilogue chunk
 constexpr int STG_LD = 20;                                   // floats per row of the epilogue transpose buffer
 constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
@@ -161,8 +164,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // The epilogues evaluate Softplus through the MUFU units (ex2 / lg2 approximations, ~2^-22 relative): their error is
 // far below the 3xTF32 product error, and the IEEE expf / log1pf sequences would cost more issue slots per tile than
@@ -330,12 +333,13 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, uint32_t (&v)[C
   __syncwarp();
 }
 
-// All chunks of one accumulator that belong to this warp (quadrant q = warp % 4, chunks c = warp / 4, +2, ...).
+// All chunks of one accumulator that belong to this warp (quadrant q = warp % 4, chunks c = warp / 4, + EPI_WARPS / 4, ...).
 // `release` is called by every lane right after the warp's last TMEM read (frees the accumulator for the MMA warp).
 template <int EPI, typename Release>
 __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_acc, int w, float* stg, int warp, int lane,
                                               int64_t row_base, int col_base, bool vec_ok, bool vec_y, YPrev& y_cur,
                                               Release release) {
+  constexpr int STEP = EPI_WARPS / 4;
   const int q = warp & 3, first = warp >> 2;
   const int nch = (w + CH - 1) / CH;
   const int64_t row0 = row_base + q * 32;
@@ -343,14 +347,39 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
     release();
     return;
   }
-  for (int c = first; c < nch; c += 2) {
-    uint32_t v[CH];
-    tmem_ld16(tmem_acc + uint32_t(c * CH) + (uint32_t(q * 32) << 16), v);
-    if (c + 2 >= nch) release();
+  if constexpr (EPI == EPI_DGRAD) {
+    // the derivative operand of the next chunk is what is kept in flight here (registers do not allow both)
+    for (int c = first; c < nch; c += STEP) {
+      uint32_t v[CH];
+      tmem_ld16(tmem_acc + uint32_t(c * CH) + (uint32_t(q * 32) << 16), v);
+      tmem_ld_wait();
+      if (c + STEP >= nch) release();
+      YPrev y_next;
+      if (c + STEP < nch) load_yprev<EPI>(e, y_next, lane, row0, col_base + (c + STEP) * CH, vec_y);
+      epilogue_chunk<EPI>(e, v, stg, y_cur, lane, row0, col_base + c * CH, vec_ok);
+      if (c + STEP < nch) y_cur = y_next;
+    }
+    return;
+  }
+  // software pipeline over the warp's chunks: the TMEM read of chunk c + STEP is in flight while chunk c is processed
+  uint32_t va[CH], vb[CH];
+  tmem_ld16(tmem_acc + uint32_t(first * CH) + (uint32_t(q * 32) << 16), va);
+  for (int c = first; c < nch; c += 2 * STEP) {
+    const int c1 = c + STEP, c2 = c + 2 * STEP;
+    tmem_ld_wait();
+    if (c1 < nch) tmem_ld16(tmem_acc + uint32_t(c1 * CH) + (uint32_t(q * 32) << 16), vb);
+    else release();
     YPrev y_next;
-    if (c + 2 < nch) load_yprev<EPI>(e, y_next, lane, row0, col_base + (c + 2) * CH, vec_y);
-    epilogue_chunk<EPI>(e, v, stg, y_cur, lane, row0, col_base + c * CH, vec_ok);
-    if (c + 2 < nch) y_cur = y_next;
+    if (c1 < nch) load_yprev<EPI>(e, y_next, lane, row0, col_base + c1 * CH, vec_y);
+    epilogue_chunk<EPI>(e, va, stg, y_cur, lane, row0, col_base + c * CH, vec_ok);
+    if (c1 >= nch) break;
+    y_cur = y_next;
+    tmem_ld_wait();
+    if (c2 < nch) tmem_ld16(tmem_acc + uint32_t(c2 * CH) + (uint32_t(q * 32) << 16), va);
+    else release();
+    if (c2 < nch) load_yprev<EPI>(e, y_next, lane, row0, col_base + c2 * CH, vec_y);
+    epilogue_chunk<EPI>(e, vb, stg, y_cur, lane, row0, col_base + c1 * CH, vec_ok);
+    if (c2 < nch) y_cur = y_next;
   }
 }
 
@@ -360,6 +389,7 @@ struct RowsArgs {
   const float* Bp; int N;
   EpiArgs epi;
   int n_tiles; int nkb; int64_t total_tiles;
+  int dbg;   // dev only (MMSB_TC_DEBUG): 1 = no A loads, 2 = no output stores, 4 = no B copies, 8 = no MMAs
 };
 
 template <int NPARTS, int EPI>
@@ -377,12 +407,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g) {
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   if (t == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(bar_full + 8 * s, PROD_THREADS + 1);
+      mbar_init(bar_full + 8 * s, 4 + 1);                // the four warps of one producer group + the B loader's expect_tx
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, EPI_WARPS * 32);
+      mbar_init(bar_tempty + 8 * a, EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -414,52 +444,56 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g) {
       load_yprev<EPI>(g.epi, y_cur, lane, mt * TM + (warp & 3) * 32, nt * NT + (warp >> 2) * CH, vec_y);
       mbar_wait(bar_tfull + 8 * acc, (ti >> 1) & 1);
       tc_fence_after();
-      epilogue_tile<EPI>(g.epi, tmem + acc * NT, w, stg, warp, lane, mt * TM, nt * NT, vec_ok, vec_y, y_cur, [&]() {
+      EpiArgs e_dbg = g.epi;
+      if (g.dbg & 2) e_dbg.M = 0;
+      epilogue_tile<EPI>(e_dbg, tmem + acc * NT, w, stg, warp, lane, mt * TM, nt * NT, vec_ok, vec_y, y_cur, [&]() {
+        // one arrival per warp: 256 single-thread arrivals on one mbarrier serialise in the shared-memory atomics
         tc_fence_before();
-        mbar_arrive(bar_tempty + 8 * acc);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       });
     }
   } else if (warp < EPI_WARPS + PROD_WARPS) {
     // ================= producers: A (global fp32) -> hi/lo -> swizzled shared memory =================
-    // A ring of LOOKAHEAD register buffers keeps the global loads of the next k-blocks in flight while the current
-    // one is split and stored: one k-block of MMAs (~0.8 us) is shorter than a loaded HBM round trip.
-    constexpr int LOOKAHEAD = 3;
+    // Two groups of four warps alternate over the k-blocks, each group owning one of the S = 2 stages (its own
+    // mbarrier phases in order): a group's loads for its next k-block are in flight while the other group stores
+    // and the MMAs of its previous block run.  (A register ring inside one warp does not pipeline: the loads of all
+    // ring slots share scoreboard entries, so the wait for the oldest slot also waits for the newest.  More groups
+    // than stages would alias the mbarrier phase parities.)
+    constexpr int GROUPS = PROD_WARPS / 4;
+    static_assert(GROUPS == 2 && S % GROUPS == 0, "a producer group must always meet the same stages");
     const int p = t - EPI_WARPS * 32;
-    const int c = p & 7, r_base = p >> 3;
+    const int grp = p >> 7, q = p & 127;
+    const int c = q & 7, r_base = q >> 3;          // 16-byte chunk c of rows r_base + 16 i
     const bool vec = ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
-    float4 v[LOOKAHEAD][4];
-    int64_t tile_l = blockIdx.x;   // load cursor (runs LOOKAHEAD k-blocks ahead of the store cursor)
-    int kb_l = 0;
-    auto load_next = [&](float4 (&dst)[4]) {
-      if (tile_l < g.total_tiles) {
-        const int64_t m0 = (tile_l / g.n_tiles) * TM;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = load4(g.A, g.lda, m0 + r_base + 32 * i, g.M, kb_l * TK + c * 4, g.K, vec);
-        if (++kb_l == g.nkb) { kb_l = 0; tile_l += gridDim.x; }
-      }
-    };
-#pragma unroll
-    for (int d = 0; d < LOOKAHEAD; ++d) load_next(v[d]);
     const int64_t my_tiles = blockIdx.x < g.total_tiles ? (g.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t iters = my_tiles * g.nkb;
-    for (int64_t it0 = 0; it0 < iters; it0 += LOOKAHEAD) {
+    float4 v[8];
+    auto load_block = [&](int64_t it) {
+      const int64_t tl = it / g.nkb;
+      const int kb = int(it - tl * g.nkb);
+      const int64_t m0 = ((blockIdx.x + tl * gridDim.x) / g.n_tiles) * TM;
 #pragma unroll
-      for (int d = 0; d < LOOKAHEAD; ++d) {
-        const int64_t it = it0 + d;
-        if (it < iters) {
-          const uint32_t s = uint32_t(it % S);
-          mbar_wait(bar_empty + 8 * s, (uint32_t(it / S) & 1) ^ 1);
-          uint8_t* a_hi = smem + s * STAGE;
+      for (int i = 0; i < 8; ++i)
+        v[i] = (g.dbg & 1) ? make_float4(1.f, 2.f, 3.f, 4.f)
+                           : load4(g.A, g.lda, m0 + r_base + 16 * i, g.M, kb * TK + c * 4, g.K, vec);
+    };
+    int64_t it = grp;
+    if (it < iters) load_block(it);
+    while (it < iters) {
+      const uint32_t s = uint32_t(it % S);
+      mbar_wait(bar_empty + 8 * s, (uint32_t(it / S) & 1) ^ 1);
+      uint8_t* a_hi = smem + s * STAGE;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = r_base + 32 * i;
-            split_store4<NPARTS>(a_hi, a_hi + PART, uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4), v[d][i]);
-          }
-          fence_async_smem();
-          mbar_arrive(bar_full + 8 * s);
-          load_next(v[d]);
-        }
+      for (int i = 0; i < 8; ++i) {
+        const int r = r_base + 16 * i;
+        split_store4<NPARTS>(a_hi, a_hi + PART, uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4), v[i]);
       }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);     // one arrival per warp (128 single arrivals would serialise)
+      it += GROUPS;
+      if (it < iters) load_block(it);
     }
   } else if (warp == EPI_WARPS + PROD_WARPS) {
     // ================= B loader: one bulk async copy per k-block =================
@@ -473,8 +507,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g) {
         for (int kb = 0; kb < g.nkb; ++kb, ++it) {
           const uint32_t s = it % S;
           mbar_wait(bar_empty + 8 * s, ((it / S) & 1) ^ 1);
-          mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
-          bulk_g2s(smem_u32(smem + s * STAGE + NPARTS * PART), src + int64_t(kb) * NPARTS * w * TK, bytes, bar_full + 8 * s);
+          if (g.dbg & 4) {
+            mbar_arrive(bar_full + 8 * s);
+          } else {
+            mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
+            bulk_g2s(smem_u32(smem + s * STAGE + NPARTS * PART), src + int64_t(kb) * NPARTS * w * TK, bytes, bar_full + 8 * s);
+          }
         }
       }
     }
@@ -498,7 +536,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g) {
           const uint32_t b_hi = a_hi + NPARTS * PART;
           const uint64_t dah = make_desc(a_hi, 16, 1024), dal = make_desc(a_hi + PART, 16, 1024);
           const uint64_t dbh = make_desc(b_hi, 16, 1024), dbl = make_desc(b_hi + w * 128, 16, 1024);
-          const int ksteps = kb == g.nkb - 1 ? last_ksteps : TK / 8;
+          const int ksteps = (g.dbg & 8) ? 0 : (kb == g.nkb - 1 ? last_ksteps : TK / 8);
           for (int j = 0; j < ksteps; ++j) {
             const uint64_t adv = uint64_t(j * 2);   // 8 tf32 = 32 bytes along K inside the swizzle row
             if (NPARTS == 2) {
@@ -531,7 +569,7 @@ struct WgradArgs {
 };
 
 template <int NPARTS>
-__global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const WgradArgs g) {
+__global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs g) {
   constexpr int S = num_stages(NPARTS);
   constexpr int STAGE = stage_bytes(NPARTS);
   extern __shared__ uint8_t smem_raw[];
@@ -554,7 +592,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const WgradArgs g)
 
   if (t == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(bar_full + 8 * s, (EPI_WARPS + PROD_WARPS) * 32);
+      mbar_init(bar_full + 8 * s, WG_STAGE_WARPS / 2);       // one arrival per warp of the staging group
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_tfull, 1);
@@ -571,60 +609,51 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const WgradArgs g)
   const uint32_t tmem = *tmem_slot;
 
   if (nkb > 0) {
-    if (warp < EPI_WARPS + PROD_WARPS) {
+    if (warp < WG_STAGE_WARPS) {
       // ================= producers: dz and x rows -> hi/lo -> MN-major swizzled shared memory =================
-      // all 16 non-issuing warps stage operands during the mainloop (the 8 epilogue warps have nothing else to do
-      // until the accumulator is complete); LOOKAHEAD register buffers keep the next k-blocks' loads in flight
-      constexpr int LOOKAHEAD = 2;
-      constexpr int NPROD = (EPI_WARPS + PROD_WARPS) * 32;   // 512
-      const int ca = t & 31, ka = t >> 5;      // dz tile: 32 chunks per k-row, k-rows ka + 16 i (i < 2)
-      const int cb = t & 63, kbb = t >> 6;     // x tile : up to 64 chunks per k-row, k-rows kbb + 8 i (i < 4)
-      static_assert(NPROD == 512, "producer mapping assumes 512 threads");
+      // Two groups of eight warps alternate over the k-blocks, each owning its stages (see tc_rows_kernel): the loads
+      // of a group's next k-block are in flight while the other group stores and the MMAs of its previous block run.
+      constexpr int GROUPS = 2;
+      static_assert(S % GROUPS == 0, "a staging group must always meet the same stages");
+      const int grp = t >> 8, q = t & 255;
+      const int ca = q & 31, ka = q >> 5;      // dz tile: 32 chunks per k-row, k-rows ka + 8 i (i < 4)
+      const int cb = q & 63, kbb = q >> 6;     // x tile : up to 64 chunks per k-row, k-rows kbb + 4 i (i < 8)
       const bool vec_a = ((g.lddz & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.dz) & 15) == 0);
       const bool vec_b = ((g.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.x) & 15) == 0);
       const bool b_active = cb < cpr;
       const bool want_db = g.db != nullptr && nt == 0;
       float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 va[LOOKAHEAD][2], vb[LOOKAHEAD][4];
-      auto load_block = [&](int kb, float4 (&a)[2], float4 (&b)[4]) {
-        if (kb >= nkb) return;
+      float4 va[4], vb[8];
+      auto load_block = [&](int kb) {
         const int64_t k0 = k_beg + int64_t(kb) * TK;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) a[i] = load4(g.dz, g.lddz, k0 + ka + 16 * i, k_end, m0 + ca * 4, g.out_dim, vec_a);
+        for (int i = 0; i < 4; ++i) va[i] = load4(g.dz, g.lddz, k0 + ka + 8 * i, k_end, m0 + ca * 4, g.out_dim, vec_a);
         if (b_active) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) b[i] = load4(g.x, g.ldx, k0 + kbb + 8 * i, k_end, n0 + cb * 4, g.in_dim, vec_b);
+          for (int i = 0; i < 8; ++i) vb[i] = load4(g.x, g.ldx, k0 + kbb + 4 * i, k_end, n0 + cb * 4, g.in_dim, vec_b);
         }
       };
+      int kb = grp;
+      if (kb < nkb) load_block(kb);
+      while (kb < nkb) {
+        const uint32_t s = kb % S;
+        mbar_wait(bar_empty + 8 * s, ((kb / S) & 1) ^ 1);
+        uint8_t* a_hi = smem + s * STAGE;
+        uint8_t* b_hi = a_hi + NPARTS * PART;
 #pragma unroll
-      for (int d = 0; d < LOOKAHEAD; ++d) load_block(d, va[d], vb[d]);
-      for (int kb0 = 0; kb0 < nkb; kb0 += LOOKAHEAD) {
-#pragma unroll
-        for (int d = 0; d < LOOKAHEAD; ++d) {
-          const int kb = kb0 + d;
-          if (kb < nkb) {
-            const uint32_t s = kb % S;
-            mbar_wait(bar_empty + 8 * s, ((kb / S) & 1) ^ 1);
-            uint8_t* a_hi = smem + s * STAGE;
-            uint8_t* b_hi = a_hi + NPARTS * PART;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const int k = ka + 16 * i;
-              split_store4<NPARTS>(a_hi, a_hi + PART, mn_offset(ca, k), va[d][i]);
-              colsum.x += va[d][i].x; colsum.y += va[d][i].y; colsum.z += va[d][i].z; colsum.w += va[d][i].w;
-            }
-            if (b_active) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int k = kbb + 8 * i;
-                split_store4<NPARTS>(b_hi, b_hi + b_part, mn_offset(cb, k), vb[d][i]);
-              }
-            }
-            fence_async_smem();
-            mbar_arrive(bar_full + 8 * s);
-            load_block(kb + LOOKAHEAD, va[d], vb[d]);
-          }
+        for (int i = 0; i < 4; ++i) {
+          split_store4<NPARTS>(a_hi, a_hi + PART, mn_offset(ca, ka + 8 * i), va[i]);
+          colsum.x += va[i].x; colsum.y += va[i].y; colsum.z += va[i].z; colsum.w += va[i].w;
         }
+        if (b_active) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) split_store4<NPARTS>(b_hi, b_hi + b_part, mn_offset(cb, kbb + 4 * i), vb[i]);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * s);     // one arrival per warp
+        kb += GROUPS;
+        if (kb < nkb) load_block(kb);
       }
       if (want_db) {
         // 16 warps hold partial column sums for the same 128 columns: combine through the L2
@@ -644,7 +673,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const WgradArgs g)
         YPrev y_none;
         epilogue_tile<EPI_ATOMIC>(e, tmem, w, stg, warp, lane, m0, n0, false, false, y_none, []() {});
       }
-    } else if (warp == EPI_WARPS + PROD_WARPS + 1) {
+    } else {
       // ================= MMA issuer =================
       if (lane == 0) {
         const uint32_t idesc = make_idesc_tf32(w, true);
@@ -714,7 +743,7 @@ static int launch_wgrad(const WgradArgs& g, dim3 grid, cudaStream_t s, const cha
     if (rc) return rc;
     configured = true;
   }
-  kern<<<grid, THREADS, smem_bytes(NPARTS), s>>>(g);
+  kern<<<grid, WG_THREADS, smem_bytes(NPARTS), s>>>(g);
   return check_launch(what);
 }
 
@@ -756,6 +785,7 @@ extern "C" int mmsb_linear_fwd_tc(const float* x, int64_t ldx, const float* pack
   g.epi.C = y; g.epi.ldc = ldy; g.epi.M = n; g.epi.N = out_dim; g.epi.bias = b; g.epi.act = act; g.epi.act_param = act_param;
   g.n_tiles = int(ceil_div(tc::pad16(out_dim), tc::NT)); g.nkb = int(ceil_div(in_dim, tc::TK));
   g.total_tiles = ceil_div(n, tc::TM) * g.n_tiles;
+  { const char* e = getenv("MMSB_TC_DEBUG"); g.dbg = e ? atoi(e) : 0; }
   return precision == 3 ? tc::launch_rows<2, tc::EPI_FWD>(g, as_stream(stream), "linear_fwd_tc(3xTF32)")
                         : tc::launch_rows<1, tc::EPI_FWD>(g, as_stream(stream), "linear_fwd_tc(TF32)");
 }

@@ -1,0 +1,22 @@
+"""dev: forward layer kernel with parts of the pipeline switched off (MMSB_TC_DEBUG bit mask) to find the bound."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from multimodalstudio_b200 import ops
+n, k, o = 2097152, 256, 256
+x = torch.randn(n, k, device="cuda"); w = torch.randn(o, k, device="cuda") * 0.1; b = torch.randn(o, device="cuda")
+y = torch.empty(n, o, device="cuda")
+for prec in (3, 1):
+    pw = ops.pack_weight(w, False, prec)
+    for dbg, what in [(0, "full"), (1, "no A loads"), (2, "no stores"), (4, "no B copies"), (8, "no MMAs"), (3, "no A loads, no stores"),
+                      (7, "MMAs only"), (11, "B copies only"), (14, "A loads only"), (13, "stores only"), (15, "nothing")]:
+        os.environ["MMSB_TC_DEBUG"] = str(dbg)
+        for _ in range(2):
+            ops.linear_fwd_tc(x, pw, b, o, 1, 1.0, prec, out=y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ops.linear_fwd_tc(x, pw, b, o, 1, 1.0, prec, out=y)
+        e1.record(); torch.cuda.synchronize()
+        print(f"prec {prec} dbg {dbg:2d} {what:24s}: {e0.elapsed_time(e1) / 5:.3f} ms", flush=True)
