@@ -152,6 +152,30 @@ int mmsb_linear_bwd_data_tc(const float* dz, int64_t lddz, const float* packed_w
 int mmsb_linear_bwd_weight_tc(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw, float* db,
                               int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision, mmsb_stream_t stream);
 
+/* The same three products for a layer that is followed by a ONE-output head (the sdf column of the last SDF layer,
+ * surface_field.py:70-72 / surface_model.py:143-146: the tap and sampler evaluations keep only output 0), fused so that
+ * the head never runs as a layer of its own:
+ *   forward : y = act(x W^T + b) (y == NULL: not stored), head_out[row] += y[row, :] . head_w (+ head_b[0]);
+ *             head_out must be zeroed by the caller (two commutative additions per row: order-independent);
+ *   dgrad   : the operand dz = head_d[row] * head_w[col] * act'(y[row, col]) is generated from the stored y;
+ *   wgrad   : likewise, and dhead_w[col] += sum_row head_d[row] * y[row, col] (the head's weight gradient);
+ *   rank1   : plain dgrad of the layer ABOVE a head-carrying layer, whose input gradient also receives the head's
+ *             rank-1 term: dx = (dz W + head_d[row] * head_w[col]) * act_prev'(y_prev). */
+int mmsb_linear_fwd_head_tc(const float* x, int64_t ldx, const float* packed_w, const float* b, float* y, int64_t ldy,
+                            int64_t n, int32_t in_dim, int32_t out_dim, int32_t act, float act_param, int32_t precision,
+                            const float* head_w, const float* head_b, float* head_out, mmsb_stream_t stream);
+int mmsb_linear_bwd_data_head_tc(const float* y, int64_t ldy, int32_t act, float act_param, const float* head_d,
+                                 const float* head_w, const float* packed_wt, float* dx, int64_t lddx, const float* y_prev,
+                                 int64_t ld_yprev, int32_t act_prev, float act_prev_param, int64_t n, int32_t in_dim,
+                                 int32_t out_dim, int32_t precision, mmsb_stream_t stream);
+int mmsb_linear_bwd_weight_head_tc(const float* y, int64_t ldy, int32_t act, float act_param, const float* head_d,
+                                   const float* head_w, const float* x, int64_t ldx, float* dw, float* db, float* dhead_w,
+                                   int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision, mmsb_stream_t stream);
+int mmsb_linear_bwd_data_rank1_tc(const float* dz, int64_t lddz, const float* packed_wt, float* dx, int64_t lddx,
+                                  const float* y_prev, int64_t ld_yprev, int32_t act_prev, float act_prev_param, int64_t n,
+                                  int32_t in_dim, int32_t out_dim, int32_t precision, const float* head_d,
+                                  const float* head_w, mmsb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * A1/A2  ray generation.  ref: cameras/camera_optimizers.py:86-119, cameras/lie_groups.py:28-63,
  * model_components/ray_generators.py:54-81, cameras/cameras.py:460-703,

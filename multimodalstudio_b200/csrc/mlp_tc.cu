@@ -237,6 +237,11 @@ struct EpiArgs {
   float* C; int64_t ldc; int64_t M; int N;   // logical extents of C
   const float* bias; int act; float act_param;
   const float* yprev; int64_t ld_yprev; int act_prev; float act_prev_param;
+  // forward with a fused one-output head: head_out[row] += sum_col act(z)[row, col] * head_w[col] (+ head_b once);
+  // C may be NULL (the activations themselves are then not stored)
+  const float* head_w; const float* head_b; float* head_out;
+  // dgrad with a rank-1 term: (acc + r1_d[row] * r1_w[col]) * act'(yprev)
+  const float* r1_d; const float* r1_w;
 };
 
 template <int ACT>
@@ -256,11 +261,20 @@ __device__ __forceinline__ float4 act_bwd4(float4 y, float p) {
 // float4 and a warp's global accesses cover 64 contiguous bytes of 8 rows.
 struct YPrev {
   float4 v[4];
+  float d[4];    // rank-1 row factors (EpiArgs::r1_d) of the 4 rows
 };
 
 template <int EPI>
 __device__ __forceinline__ void load_yprev(const EpiArgs& e, YPrev& y, int lane, int64_t row0, int col0, bool vec_y) {
-  if (EPI != EPI_DGRAD || e.yprev == nullptr || e.act_prev == MMSB_ACT_NONE) return;
+  if (EPI != EPI_DGRAD) return;
+  if (e.r1_d) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t row = row0 + (lane >> 2) + 8 * i;
+      y.d[i] = row < e.M ? __ldg(e.r1_d + row) : 0.f;
+    }
+  }
+  if (e.yprev == nullptr || e.act_prev == MMSB_ACT_NONE) return;
   const int col = col0 + 4 * (lane & 3);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -269,20 +283,30 @@ __device__ __forceinline__ void load_yprev(const EpiArgs& e, YPrev& y, int lane,
   }
 }
 
+// 4 values of a per-column vector at col..col+3 (zero past n)
+__device__ __forceinline__ float4 load_cols4(const float* __restrict__ p, int col, int n) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p == nullptr) return v;
+  v.x = __ldg(p + col);
+  if (col + 1 < n) v.y = __ldg(p + col + 1);
+  if (col + 2 < n) v.z = __ldg(p + col + 2);
+  if (col + 3 < n) v.w = __ldg(p + col + 3);
+  return v;
+}
+
 template <int EPI, int ACT>
 __device__ __forceinline__ void epilogue_rows(const EpiArgs& e, const float* stg, const YPrev& yp, int lane, int64_t row0,
-                                              int col0, bool vec_ok) {
+                                              int col0, bool vec_ok, float (&hacc)[4]) {
   const int q4 = lane & 3;
   const int col = col0 + 4 * q4;
   if (col >= e.N) return;
   const bool full = col + 3 < e.N;
-  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (EPI == EPI_FWD && e.bias) {
-    b4.x = __ldg(e.bias + col);
-    if (col + 1 < e.N) b4.y = __ldg(e.bias + col + 1);
-    if (col + 2 < e.N) b4.z = __ldg(e.bias + col + 2);
-    if (col + 3 < e.N) b4.w = __ldg(e.bias + col + 3);
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), h4 = b4, r4 = b4;
+  if (EPI == EPI_FWD) {
+    b4 = load_cols4(e.bias, col, e.N);
+    h4 = load_cols4(e.head_w, col, e.N);
   }
+  if (EPI == EPI_DGRAD) r4 = load_cols4(e.r1_w, col, e.N);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = (lane >> 2) + 8 * i;
@@ -293,9 +317,19 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& e, const float* stg
     if (EPI == EPI_FWD) {
       x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
       x = act_fwd4<ACT>(x, e.act_param);
-    } else if (EPI == EPI_DGRAD && ACT != MMSB_ACT_NONE) {
-      const float4 y = act_bwd4<ACT>(yp.v[i], e.act_prev_param);
-      x.x *= y.x; x.y *= y.y; x.z *= y.z; x.w *= y.w;
+      if (e.head_w) {
+        hacc[i] = fmaf(x.x, h4.x, fmaf(x.y, h4.y, fmaf(x.z, h4.z, fmaf(x.w, h4.w, hacc[i]))));
+        if (e.C == nullptr) continue;
+      }
+    } else if (EPI == EPI_DGRAD) {
+      if (e.r1_d) {
+        const float d = yp.d[i];
+        x.x = fmaf(d, r4.x, x.x); x.y = fmaf(d, r4.y, x.y); x.z = fmaf(d, r4.z, x.z); x.w = fmaf(d, r4.w, x.w);
+      }
+      if (ACT != MMSB_ACT_NONE) {
+        const float4 y = act_bwd4<ACT>(yp.v[i], e.act_prev_param);
+        x.x *= y.x; x.y *= y.y; x.z *= y.z; x.w *= y.w;
+      }
     }
     if (EPI == EPI_ATOMIC) {
       atomicAdd(dst, x.x);
@@ -316,7 +350,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& e, const float* stg
 // One chunk: lane owns row (row0 + lane) in registers -> transpose buffer -> epilogue_rows.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, uint32_t (&v)[CH], float* stg, const YPrev& yp, int lane,
-                                               int64_t row0, int col0, bool vec_ok) {
+                                               int64_t row0, int col0, bool vec_ok, float (&hacc)[4]) {
 #pragma unroll
   for (int j = 0; j < CH / 4; ++j)
     *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) =
@@ -325,10 +359,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, uint32_t (&v)[C
   __syncwarp();
   const int act = EPI == EPI_FWD ? e.act : (EPI == EPI_DGRAD && e.yprev ? e.act_prev : MMSB_ACT_NONE);
   switch (act) {
-    case MMSB_ACT_RELU: epilogue_rows<EPI, MMSB_ACT_RELU>(e, stg, yp, lane, row0, col0, vec_ok); break;
-    case MMSB_ACT_SOFTPLUS: epilogue_rows<EPI, MMSB_ACT_SOFTPLUS>(e, stg, yp, lane, row0, col0, vec_ok); break;
-    case MMSB_ACT_SIGMOID: epilogue_rows<EPI, MMSB_ACT_SIGMOID>(e, stg, yp, lane, row0, col0, vec_ok); break;
-    default: epilogue_rows<EPI, MMSB_ACT_NONE>(e, stg, yp, lane, row0, col0, vec_ok); break;
+    case MMSB_ACT_RELU: epilogue_rows<EPI, MMSB_ACT_RELU>(e, stg, yp, lane, row0, col0, vec_ok, hacc); break;
+    case MMSB_ACT_SOFTPLUS: epilogue_rows<EPI, MMSB_ACT_SOFTPLUS>(e, stg, yp, lane, row0, col0, vec_ok, hacc); break;
+    case MMSB_ACT_SIGMOID: epilogue_rows<EPI, MMSB_ACT_SIGMOID>(e, stg, yp, lane, row0, col0, vec_ok, hacc); break;
+    default: epilogue_rows<EPI, MMSB_ACT_NONE>(e, stg, yp, lane, row0, col0, vec_ok, hacc); break;
   }
   __syncwarp();
 }
@@ -343,6 +377,23 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
   const int q = warp & 3, first = warp >> 2;
   const int nch = (w + CH - 1) / CH;
   const int64_t row0 = row_base + q * 32;
+  float hacc[4] = {0.f, 0.f, 0.f, 0.f};
+  // fused head: the four lanes that share a row combine their partial dot products; one reduction per row and warp
+  // (two warps per row -> two commutative additions onto the caller's zeros: order-independent)
+  auto head_flush = [&]() {
+    if (EPI != EPI_FWD || e.head_w == nullptr) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v = hacc[i];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      const int64_t row = row0 + (lane >> 2) + 8 * i;
+      if ((lane & 3) == 0 && row < e.M) {
+        if (first == 0 && col_base == 0 && e.head_b) v += __ldg(e.head_b);
+        atomicAdd(e.head_out + row, v);
+      }
+    }
+  };
   if (first >= nch) {
     release();
     return;
@@ -356,7 +407,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
       if (c + STEP >= nch) release();
       YPrev y_next;
       if (c + STEP < nch) load_yprev<EPI>(e, y_next, lane, row0, col_base + (c + STEP) * CH, vec_y);
-      epilogue_chunk<EPI>(e, v, stg, y_cur, lane, row0, col_base + c * CH, vec_ok);
+      epilogue_chunk<EPI>(e, v, stg, y_cur, lane, row0, col_base + c * CH, vec_ok, hacc);
       if (c + STEP < nch) y_cur = y_next;
     }
     return;
@@ -371,16 +422,17 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
     else release();
     YPrev y_next;
     if (c1 < nch) load_yprev<EPI>(e, y_next, lane, row0, col_base + c1 * CH, vec_y);
-    epilogue_chunk<EPI>(e, va, stg, y_cur, lane, row0, col_base + c * CH, vec_ok);
+    epilogue_chunk<EPI>(e, va, stg, y_cur, lane, row0, col_base + c * CH, vec_ok, hacc);
     if (c1 >= nch) break;
     y_cur = y_next;
     tmem_ld_wait();
     if (c2 < nch) tmem_ld16(tmem_acc + uint32_t(c2 * CH) + (uint32_t(q * 32) << 16), va);
     else release();
     if (c2 < nch) load_yprev<EPI>(e, y_next, lane, row0, col_base + c2 * CH, vec_y);
-    epilogue_chunk<EPI>(e, vb, stg, y_cur, lane, row0, col_base + c1 * CH, vec_ok);
+    epilogue_chunk<EPI>(e, vb, stg, y_cur, lane, row0, col_base + c1 * CH, vec_ok, hacc);
     if (c2 < nch) y_cur = y_next;
   }
+  head_flush();
 }
 
 // ---- forward / dgrad ----------------------------------------------------------------------------------------
@@ -390,6 +442,9 @@ struct RowsArgs {
   EpiArgs epi;
   int n_tiles; int nkb; int64_t total_tiles;
   int dbg;   // dev only (MMSB_TC_DEBUG): 1 = no A loads, 2 = no output stores, 4 = no B copies, 8 = no MMAs
+  // generated operand (dgrad below a fused head): A[r, k] = hd[r] * hw[k] * act'(A_mem[r, k]), A_mem = the stored
+  // activations of the layer
+  const float* hd; const float* hw; int hact; float hact_param;
 };
 
 template <int NPARTS, int EPI>
@@ -469,6 +524,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g) {
     const int64_t my_tiles = blockIdx.x < g.total_tiles ? (g.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t iters = my_tiles * g.nkb;
     float4 v[8];
+    float hd[8];
+    float4 hw4 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto load_block = [&](int64_t it) {
       const int64_t tl = it / g.nkb;
       const int kb = int(it - tl * g.nkb);
@@ -477,6 +534,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g) {
       for (int i = 0; i < 8; ++i)
         v[i] = (g.dbg & 1) ? make_float4(1.f, 2.f, 3.f, 4.f)
                            : load4(g.A, g.lda, m0 + r_base + 16 * i, g.M, kb * TK + c * 4, g.K, vec);
+      if (g.hd) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t row = m0 + r_base + 16 * i;
+          hd[i] = row < g.M ? __ldg(g.hd + row) : 0.f;
+        }
+        hw4 = kb * TK + c * 4 < g.K ? load_cols4(g.hw, kb * TK + c * 4, g.K) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto generate = [&](float4 y, float d) {
+      float4 a;
+      a.x = d * hw4.x * act_bwd_from_y(y.x, g.hact, g.hact_param);
+      a.y = d * hw4.y * act_bwd_from_y(y.y, g.hact, g.hact_param);
+      a.z = d * hw4.z * act_bwd_from_y(y.z, g.hact, g.hact_param);
+      a.w = d * hw4.w * act_bwd_from_y(y.w, g.hact, g.hact_param);
+      return a;
     };
     int64_t it = grp;
     if (it < iters) load_block(it);
@@ -487,7 +560,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = r_base + 16 * i;
-        split_store4<NPARTS>(a_hi, a_hi + PART, uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4), v[i]);
+        split_store4<NPARTS>(a_hi, a_hi + PART, uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4),
+                             g.hd ? generate(v[i], hd[i]) : v[i]);
       }
       fence_async_smem();
       __syncwarp();
@@ -566,6 +640,9 @@ struct WgradArgs {
   const float* x; int64_t ldx; int in_dim;
   float* dw; int64_t lddw; float* db;
   int64_t rows; int64_t rows_per_split; int n_tiles;
+  // generated dz (weight gradient below a fused head): dz[r, c] = hd[r] * hw[c] * act'(dz_mem[r, c]) with dz_mem = the
+  // stored activations y of the layer; dhw[c] += sum_r hd[r] * y[r, c] (the head's own weight gradient)
+  const float* hd; const float* hw; int hact; float hact_param; float* dhw;
 };
 
 template <int NPARTS>
@@ -622,10 +699,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
       const bool vec_b = ((g.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.x) & 15) == 0);
       const bool b_active = cb < cpr;
       const bool want_db = g.db != nullptr && nt == 0;
-      float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f), hsum = colsum;
       float4 va[4], vb[8];
+      float hd[4];
+      const float4 hw4 = g.hd && m0 + ca * 4 < g.out_dim ? load_cols4(g.hw, m0 + ca * 4, g.out_dim) : make_float4(0.f, 0.f, 0.f, 0.f);
       auto load_block = [&](int kb) {
         const int64_t k0 = k_beg + int64_t(kb) * TK;
+        if (g.hd) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hd[i] = k0 + ka + 8 * i < k_end ? __ldg(g.hd + k0 + ka + 8 * i) : 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) va[i] = load4(g.dz, g.lddz, k0 + ka + 8 * i, k_end, m0 + ca * 4, g.out_dim, vec_a);
         if (b_active) {
@@ -642,6 +725,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
         uint8_t* b_hi = a_hi + NPARTS * PART;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          if (g.hd) {
+            const float4 y = va[i];
+            const float d = hd[i];
+            hsum.x = fmaf(d, y.x, hsum.x); hsum.y = fmaf(d, y.y, hsum.y); hsum.z = fmaf(d, y.z, hsum.z); hsum.w = fmaf(d, y.w, hsum.w);
+            va[i].x = d * hw4.x * act_bwd_from_y(y.x, g.hact, g.hact_param);
+            va[i].y = d * hw4.y * act_bwd_from_y(y.y, g.hact, g.hact_param);
+            va[i].z = d * hw4.z * act_bwd_from_y(y.z, g.hact, g.hact_param);
+            va[i].w = d * hw4.w * act_bwd_from_y(y.w, g.hact, g.hact_param);
+          }
           split_store4<NPARTS>(a_hi, a_hi + PART, mn_offset(ca, ka + 8 * i), va[i]);
           colsum.x += va[i].x; colsum.y += va[i].y; colsum.z += va[i].z; colsum.w += va[i].w;
         }
@@ -662,6 +754,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
         if (col + 1 < g.out_dim) atomicAdd(g.db + col + 1, colsum.y);
         if (col + 2 < g.out_dim) atomicAdd(g.db + col + 2, colsum.z);
         if (col + 3 < g.out_dim) atomicAdd(g.db + col + 3, colsum.w);
+      }
+      if (g.hd && g.dhw && nt == 0) {
+        const int col = m0 + ca * 4;
+        if (col < g.out_dim) atomicAdd(g.dhw + col, hsum.x);
+        if (col + 1 < g.out_dim) atomicAdd(g.dhw + col + 1, hsum.y);
+        if (col + 2 < g.out_dim) atomicAdd(g.dhw + col + 2, hsum.z);
+        if (col + 3 < g.out_dim) atomicAdd(g.dhw + col + 3, hsum.w);
       }
       if (warp < EPI_WARPS) {
         // ================= epilogue: partial tile -> dW with coalesced reductions =================
@@ -772,51 +871,42 @@ extern "C" int mmsb_linear_pack_weight(const float* w, int64_t ldw, int32_t out_
   return check_launch("linear_pack_weight");
 }
 
-extern "C" int mmsb_linear_fwd_tc(const float* x, int64_t ldx, const float* packed_w, const float* b, float* y, int64_t ldy,
-                                  int64_t n, int32_t in_dim, int32_t out_dim, int32_t act, float act_param, int32_t precision,
-                                  mmsb_stream_t stream) {
-  MMSB_REQUIRE(x && packed_w && y, "linear_fwd_tc: null pointer");
-  MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && ldx >= in_dim && ldy >= out_dim, "linear_fwd_tc: bad shape");
-  MMSB_REQUIRE(act >= MMSB_ACT_NONE && act <= MMSB_ACT_SIGMOID, "linear_fwd_tc: unknown activation %d", act);
-  MMSB_REQUIRE(valid_precision(precision), "linear_fwd_tc: precision must be 1 or 3, got %d", precision);
-  if (n == 0) return MMSB_OK;
+// ---- internal launch helpers shared by the plain and the fused-head entry points ----------------------------------
+static int rows_fwd(const float* x, int64_t ldx, const float* packed_w, const float* b, float* y, int64_t ldy, int64_t n,
+                    int in_dim, int out_dim, int act, float act_param, int precision, const float* head_w,
+                    const float* head_b, float* head_out, cudaStream_t stream, const char* what) {
   tc::RowsArgs g{};
   g.A = x; g.lda = ldx; g.M = n; g.K = in_dim; g.Bp = packed_w; g.N = out_dim;
   g.epi.C = y; g.epi.ldc = ldy; g.epi.M = n; g.epi.N = out_dim; g.epi.bias = b; g.epi.act = act; g.epi.act_param = act_param;
+  g.epi.head_w = head_w; g.epi.head_b = head_b; g.epi.head_out = head_out;
   g.n_tiles = int(ceil_div(tc::pad16(out_dim), tc::NT)); g.nkb = int(ceil_div(in_dim, tc::TK));
   g.total_tiles = ceil_div(n, tc::TM) * g.n_tiles;
   { const char* e = getenv("MMSB_TC_DEBUG"); g.dbg = e ? atoi(e) : 0; }
-  return precision == 3 ? tc::launch_rows<2, tc::EPI_FWD>(g, as_stream(stream), "linear_fwd_tc(3xTF32)")
-                        : tc::launch_rows<1, tc::EPI_FWD>(g, as_stream(stream), "linear_fwd_tc(TF32)");
+  return precision == 3 ? tc::launch_rows<2, tc::EPI_FWD>(g, stream, what) : tc::launch_rows<1, tc::EPI_FWD>(g, stream, what);
 }
 
-extern "C" int mmsb_linear_bwd_data_tc(const float* dz, int64_t lddz, const float* packed_wt, float* dx, int64_t lddx,
-                                       const float* y_prev, int64_t ld_yprev, int32_t act_prev, float act_prev_param,
-                                       int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision, mmsb_stream_t stream) {
-  MMSB_REQUIRE(dz && packed_wt && dx, "linear_bwd_data_tc: null pointer");
-  MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && lddz >= out_dim && lddx >= in_dim, "linear_bwd_data_tc: bad shape");
-  MMSB_REQUIRE(valid_precision(precision), "linear_bwd_data_tc: precision must be 1 or 3, got %d", precision);
-  if (n == 0) return MMSB_OK;
+static int rows_dgrad(const float* a, int64_t lda, const float* packed_wt, float* dx, int64_t lddx, const float* y_prev,
+                      int64_t ld_yprev, int act_prev, float act_prev_param, int64_t n, int in_dim, int out_dim,
+                      int precision, const float* r1_d, const float* r1_w, const float* hd, const float* hw, int hact,
+                      float hact_param, cudaStream_t stream, const char* what) {
   tc::RowsArgs g{};
-  g.A = dz; g.lda = lddz; g.M = n; g.K = out_dim; g.Bp = packed_wt; g.N = in_dim;
+  g.A = a; g.lda = lda; g.M = n; g.K = out_dim; g.Bp = packed_wt; g.N = in_dim;
   g.epi.C = dx; g.epi.ldc = lddx; g.epi.M = n; g.epi.N = in_dim;
   g.epi.yprev = y_prev; g.epi.ld_yprev = ld_yprev; g.epi.act_prev = act_prev; g.epi.act_prev_param = act_prev_param;
+  g.epi.r1_d = r1_d; g.epi.r1_w = r1_w;
+  g.hd = hd; g.hw = hw; g.hact = hact; g.hact_param = hact_param;
   g.n_tiles = int(ceil_div(tc::pad16(in_dim), tc::NT)); g.nkb = int(ceil_div(out_dim, tc::TK));
   g.total_tiles = ceil_div(n, tc::TM) * g.n_tiles;
-  return precision == 3 ? tc::launch_rows<2, tc::EPI_DGRAD>(g, as_stream(stream), "linear_bwd_data_tc(3xTF32)")
-                        : tc::launch_rows<1, tc::EPI_DGRAD>(g, as_stream(stream), "linear_bwd_data_tc(TF32)");
+  return precision == 3 ? tc::launch_rows<2, tc::EPI_DGRAD>(g, stream, what) : tc::launch_rows<1, tc::EPI_DGRAD>(g, stream, what);
 }
 
-extern "C" int mmsb_linear_bwd_weight_tc(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw, float* db,
-                                         int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision,
-                                         mmsb_stream_t stream) {
-  MMSB_REQUIRE(dz && x && dw, "linear_bwd_weight_tc: null pointer");
-  MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && lddz >= out_dim && ldx >= in_dim, "linear_bwd_weight_tc: bad shape");
-  MMSB_REQUIRE(valid_precision(precision), "linear_bwd_weight_tc: precision must be 1 or 3, got %d", precision);
-  if (n == 0) return MMSB_OK;
+static int rows_wgrad(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw, float* db, int64_t n, int in_dim,
+                      int out_dim, int precision, const float* hd, const float* hw, int hact, float hact_param, float* dhw,
+                      cudaStream_t stream, const char* what) {
   tc::WgradArgs g{};
   g.dz = dz; g.lddz = lddz; g.out_dim = out_dim; g.x = x; g.ldx = ldx; g.in_dim = in_dim;
   g.dw = dw; g.lddw = in_dim; g.db = db; g.rows = n;
+  g.hd = hd; g.hw = hw; g.hact = hact; g.hact_param = hact_param; g.dhw = dhw;
   const int m_tiles = int(ceil_div(out_dim, tc::TM));
   g.n_tiles = int(ceil_div(tc::pad16(in_dim), tc::NT));
   const int tiles = m_tiles * g.n_tiles;
@@ -826,6 +916,90 @@ extern "C" int mmsb_linear_bwd_weight_tc(const float* dz, int64_t lddz, const fl
   if (splits > max_splits) splits = max_splits;
   g.rows_per_split = ceil_div(ceil_div(n, splits), tc::TK) * tc::TK;
   dim3 grid((unsigned)tiles, (unsigned)ceil_div(n, g.rows_per_split));
-  return precision == 3 ? tc::launch_wgrad<2>(g, grid, as_stream(stream), "linear_bwd_weight_tc(3xTF32)")
-                        : tc::launch_wgrad<1>(g, grid, as_stream(stream), "linear_bwd_weight_tc(TF32)");
+  return precision == 3 ? tc::launch_wgrad<2>(g, grid, stream, what) : tc::launch_wgrad<1>(g, grid, stream, what);
+}
+
+extern "C" int mmsb_linear_fwd_tc(const float* x, int64_t ldx, const float* packed_w, const float* b, float* y, int64_t ldy,
+                                  int64_t n, int32_t in_dim, int32_t out_dim, int32_t act, float act_param, int32_t precision,
+                                  mmsb_stream_t stream) {
+  MMSB_REQUIRE(x && packed_w && y, "linear_fwd_tc: null pointer");
+  MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && ldx >= in_dim && ldy >= out_dim, "linear_fwd_tc: bad shape");
+  MMSB_REQUIRE(act >= MMSB_ACT_NONE && act <= MMSB_ACT_SIGMOID, "linear_fwd_tc: unknown activation %d", act);
+  MMSB_REQUIRE(valid_precision(precision), "linear_fwd_tc: precision must be 1 or 3, got %d", precision);
+  if (n == 0) return MMSB_OK;
+  return rows_fwd(x, ldx, packed_w, b, y, ldy, n, in_dim, out_dim, act, act_param, precision, nullptr, nullptr, nullptr,
+                  as_stream(stream), "linear_fwd_tc");
+}
+
+extern "C" int mmsb_linear_fwd_head_tc(const float* x, int64_t ldx, const float* packed_w, const float* b, float* y,
+                                       int64_t ldy, int64_t n, int32_t in_dim, int32_t out_dim, int32_t act, float act_param,
+                                       int32_t precision, const float* head_w, const float* head_b, float* head_out,
+                                       mmsb_stream_t stream) {
+  MMSB_REQUIRE(x && packed_w && head_w && head_out, "linear_fwd_head_tc: null pointer");
+  MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && out_dim <= tc::NT && ldx >= in_dim && (!y || ldy >= out_dim),
+               "linear_fwd_head_tc: bad shape (the fused head needs out_dim <= 256)");
+  MMSB_REQUIRE(act >= MMSB_ACT_NONE && act <= MMSB_ACT_SIGMOID, "linear_fwd_head_tc: unknown activation %d", act);
+  MMSB_REQUIRE(valid_precision(precision), "linear_fwd_head_tc: precision must be 1 or 3, got %d", precision);
+  if (n == 0) return MMSB_OK;
+  return rows_fwd(x, ldx, packed_w, b, y, ldy, n, in_dim, out_dim, act, act_param, precision, head_w, head_b, head_out,
+                  as_stream(stream), "linear_fwd_head_tc");
+}
+
+extern "C" int mmsb_linear_bwd_data_tc(const float* dz, int64_t lddz, const float* packed_wt, float* dx, int64_t lddx,
+                                       const float* y_prev, int64_t ld_yprev, int32_t act_prev, float act_prev_param,
+                                       int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision, mmsb_stream_t stream) {
+  MMSB_REQUIRE(dz && packed_wt && dx, "linear_bwd_data_tc: null pointer");
+  MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && lddz >= out_dim && lddx >= in_dim, "linear_bwd_data_tc: bad shape");
+  MMSB_REQUIRE(valid_precision(precision), "linear_bwd_data_tc: precision must be 1 or 3, got %d", precision);
+  if (n == 0) return MMSB_OK;
+  return rows_dgrad(dz, lddz, packed_wt, dx, lddx, y_prev, ld_yprev, act_prev, act_prev_param, n, in_dim, out_dim, precision,
+                    nullptr, nullptr, nullptr, nullptr, 0, 0.f, as_stream(stream), "linear_bwd_data_tc");
+}
+
+extern "C" int mmsb_linear_bwd_data_rank1_tc(const float* dz, int64_t lddz, const float* packed_wt, float* dx, int64_t lddx,
+                                             const float* y_prev, int64_t ld_yprev, int32_t act_prev, float act_prev_param,
+                                             int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision,
+                                             const float* head_d, const float* head_w, mmsb_stream_t stream) {
+  MMSB_REQUIRE(dz && packed_wt && dx && head_d && head_w, "linear_bwd_data_rank1_tc: null pointer");
+  MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && lddz >= out_dim && lddx >= in_dim, "linear_bwd_data_rank1_tc: bad shape");
+  MMSB_REQUIRE(valid_precision(precision), "linear_bwd_data_rank1_tc: precision must be 1 or 3, got %d", precision);
+  if (n == 0) return MMSB_OK;
+  return rows_dgrad(dz, lddz, packed_wt, dx, lddx, y_prev, ld_yprev, act_prev, act_prev_param, n, in_dim, out_dim, precision,
+                    head_d, head_w, nullptr, nullptr, 0, 0.f, as_stream(stream), "linear_bwd_data_rank1_tc");
+}
+
+extern "C" int mmsb_linear_bwd_data_head_tc(const float* y, int64_t ldy, int32_t act, float act_param, const float* head_d,
+                                            const float* head_w, const float* packed_wt, float* dx, int64_t lddx,
+                                            const float* y_prev, int64_t ld_yprev, int32_t act_prev, float act_prev_param,
+                                            int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision,
+                                            mmsb_stream_t stream) {
+  MMSB_REQUIRE(y && head_d && head_w && packed_wt && dx, "linear_bwd_data_head_tc: null pointer");
+  MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && ldy >= out_dim && lddx >= in_dim, "linear_bwd_data_head_tc: bad shape");
+  MMSB_REQUIRE(valid_precision(precision), "linear_bwd_data_head_tc: precision must be 1 or 3, got %d", precision);
+  if (n == 0) return MMSB_OK;
+  return rows_dgrad(y, ldy, packed_wt, dx, lddx, y_prev, ld_yprev, act_prev, act_prev_param, n, in_dim, out_dim, precision,
+                    nullptr, nullptr, head_d, head_w, act, act_param, as_stream(stream), "linear_bwd_data_head_tc");
+}
+
+extern "C" int mmsb_linear_bwd_weight_tc(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw, float* db,
+                                         int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision,
+                                         mmsb_stream_t stream) {
+  MMSB_REQUIRE(dz && x && dw, "linear_bwd_weight_tc: null pointer");
+  MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && lddz >= out_dim && ldx >= in_dim, "linear_bwd_weight_tc: bad shape");
+  MMSB_REQUIRE(valid_precision(precision), "linear_bwd_weight_tc: precision must be 1 or 3, got %d", precision);
+  if (n == 0) return MMSB_OK;
+  return rows_wgrad(dz, lddz, x, ldx, dw, db, n, in_dim, out_dim, precision, nullptr, nullptr, 0, 0.f, nullptr,
+                    as_stream(stream), "linear_bwd_weight_tc");
+}
+
+extern "C" int mmsb_linear_bwd_weight_head_tc(const float* y, int64_t ldy, int32_t act, float act_param, const float* head_d,
+                                              const float* head_w, const float* x, int64_t ldx, float* dw, float* db,
+                                              float* dhead_w, int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision,
+                                              mmsb_stream_t stream) {
+  MMSB_REQUIRE(y && head_d && head_w && x && dw, "linear_bwd_weight_head_tc: null pointer");
+  MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && ldy >= out_dim && ldx >= in_dim, "linear_bwd_weight_head_tc: bad shape");
+  MMSB_REQUIRE(valid_precision(precision), "linear_bwd_weight_head_tc: precision must be 1 or 3, got %d", precision);
+  if (n == 0) return MMSB_OK;
+  return rows_wgrad(y, ldy, x, ldx, dw, db, n, in_dim, out_dim, precision, head_d, head_w, act, act_param, dhead_w,
+                    as_stream(stream), "linear_bwd_weight_head_tc");
 }

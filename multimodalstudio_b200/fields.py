@@ -53,7 +53,28 @@ class SDFField(SurfaceField):
         super().__init__(config)
         self.field = self.config.field.setup(input_dim=self.input_dim, output_dim=self.output_dim)
 
+    def _fused(self):
+        """The fused SDF network (ops.SdfNetFn) applies to the shipped shape: PE + hash grid, two hidden layers, no skips,
+        no output activation, tcgen05 layer path."""
+        mlp = getattr(self.field, "mlp_head", None)
+        return (ops.MLP_PRECISION != 0 and self.config.use_position_encoding and hasattr(self.field, "feature_grid")
+                and mlp is not None and len(mlp.layers) == 3 and not mlp.config.skip_connections
+                and mlp.config.out_activation in (None, "None") and self.config.geo_feature_dim is not None
+                and mlp.layers[1].out_features <= 256)
+
+    def forward_split(self, x, n_full: int):
+        """x [n, 3] -> sdf [n, 1] for every row, geo_feature [n_full, G] for the first n_full rows (one network call for
+        the centre evaluations and the finite-difference taps of surface_model.py:129-152)."""
+        mlp = self.field.mlp_head
+        rows = ops.assemble([self.position_encoding.piece(x), self.field.feature_grid.piece(x)])
+        return ops.sdf_net_forward(rows, n_full, [l.weight for l in mlp.layers], [l.bias for l in mlp.layers],
+                                   mlp.config.activation, mlp.act_param)
+
     def forward(self, x, sdf_only: bool = False):
+        if self._fused():
+            x2 = x.reshape(-1, 3)
+            sdf, geo = self.forward_split(x2, 0 if sdf_only else x2.shape[0])
+            return sdf.reshape(*x.shape[:-1], 1), (None if sdf_only else geo.reshape(*x.shape[:-1], geo.shape[-1]))
         if self.config.use_position_encoding and hasattr(self.field, "feature_grid"):
             # cat[PE(x), hash(x)] written in place by the two encoders
             kw = dict(pieces=[self.position_encoding.piece(x)], positions=x)

@@ -375,13 +375,18 @@ class SurfaceModel(nn.Module):
         if self.spatial_distortion is not None:
             inputs = self.spatial_distortion(inputs)
         n = inputs.shape[0]
-        sdf, geo_feature = self.surface_field(inputs)
         # 4 tetrahedron taps, sdf only (surface_model.py:138-146)
         delta = self.numerical_gradients_delta / np.sqrt(3)
         k = ops.const_tensor("taps4", lambda: torch.tensor([[1, -1, -1], [-1, -1, 1], [-1, 1, -1], [1, 1, 1]], dtype=torch.float32),
                              inputs.device)
         taps = (inputs[None] + k[:, None, :] * delta).reshape(-1, 3)
-        sdf_t = self.surface_field.single_output(taps).reshape(4, n)
+        if hasattr(self.surface_field, "_fused") and self.surface_field._fused():
+            # centre + taps as one batch through the network (geometry features only for the centre rows)
+            sdf_all, geo_feature = self.surface_field.forward_split(torch.cat([inputs, taps], 0), n)
+            sdf, sdf_t = sdf_all[:n], sdf_all[n:, 0].reshape(4, n)
+        else:
+            sdf, geo_feature = self.surface_field(inputs)
+            sdf_t = self.surface_field.single_output(taps).reshape(4, n)
         want_h = bool(self.training and self.config.compute_hessian)
         gradients, hessians, normals = ops.SdfTapsFn.apply(sdf[..., 0], sdf_t, float(delta), want_h)
         sdf = sdf.view(*shape, -1)

@@ -423,14 +423,17 @@ def _use_tc(w) -> bool:
     return MLP_PRECISION != 0
 
 
-def packed_weight(w, transpose: bool, precision: int):
-    """Packed operand of w, memoised per tensor object and version (valid while torch.nn.utils.parametrize.cached()
-    keeps the effective weight alive, i.e. for one step)."""
-    key = (id(w), bool(transpose), precision)
+def packed_weight(w, transpose: bool, precision: int, rows=None):
+    """Packed operand of w (or of its row range `rows` = (first, last + 1)), memoised per tensor object and version
+    (valid while torch.nn.utils.parametrize.cached() keeps the effective weight alive, i.e. for one step)."""
+    key = (id(w), bool(transpose), precision, rows)
     hit = _PACK_CACHE.get(key)
     if hit is not None and hit[0]() is w and hit[1] == w._version:
         return hit[2]
-    packed = pack_weight(_f(w.detach()), transpose, precision)
+    src = _f(w.detach())
+    if rows is not None:
+        src = src[rows[0]:rows[1]]
+    packed = pack_weight(src, transpose, precision)
     if len(_PACK_CACHE) > 512:
         _PACK_CACHE.clear()
     _PACK_CACHE[key] = (weakref.ref(w), w._version, packed)
@@ -554,6 +557,97 @@ class MLPFn(torch.autograd.Function):
             dx = dz if dx_skip is None else dz + dx_skip
             dx = dx.reshape(x_shape)
         return (dx, None, None, None, None, None, *grads)
+
+
+class SdfNetFn(torch.autograd.Function):
+    """The SDF network (surface_field.py:99-116, mlp.py:152-171) with its last layer split into the sdf head (output 0)
+    and the geometry features (outputs 1..G):  x [n, in] -> sdf [n, 1] for every row, geo [n_full, G] for the first
+    n_full rows (the centre evaluations; the tap and sampler evaluations keep only the sdf, surface_model.py:143-146).
+    The sdf head never runs as a layer: its dot product is fused into the epilogue of layer 1 and its backward into the
+    operand producers of layer 1's dgrad / wgrad (mmsb_linear_*_head_tc) — one arithmetic for centre, taps and sampler.
+    args: (x, n_full, act, act_param, W0, b0, W1, b1, W2, b2), two hidden layers."""
+
+    @staticmethod
+    def forward(ctx, x, n_full, act, act_param, w0, b0, w1, b1, w2, b2):
+        prec = MLP_PRECISION
+        if prec == 0:
+            raise RuntimeError("SdfNetFn needs the tcgen05 layer path (MLP precision 1 or 3)")
+        in_dim = x.shape[-1]
+        x2 = _rows(x, in_dim)
+        n = x2.shape[0]
+        ws = [_f(w0), _f(w1), _f(w2)]
+        bs = [_f(b0), _f(b1), _f(b2)]
+        hid = ws[1].shape[0]
+        g_dim = ws[2].shape[0] - 1
+        need_grad = any(ctx.needs_input_grad)
+        dev = x2.device
+        h0 = linear_fwd_tc(x2, packed_weight(w0, False, prec), bs[0], ws[0].shape[0], act, act_param, prec)
+        sdf = torch.zeros((n,), device=dev, dtype=torch.float32)
+        keep_h1 = need_grad or n_full > 0
+        h1 = torch.empty((n, hid), device=dev, dtype=torch.float32) if keep_h1 else None
+        call("mmsb_linear_fwd_head_tc", ptr(h0), _i64(h0.stride(0)), ptr(packed_weight(w1, False, prec)), ptr(bs[1]), ptr(h1),
+             _i64(hid), _i64(n), _i32(ws[1].shape[1]), _i32(hid), _i32(act), _f32(act_param), _i32(prec), ptr(ws[2]),
+             ptr(bs[2]), ptr(sdf), stream_ptr())
+        geo = None
+        if n_full > 0:
+            geo = linear_fwd_tc(h1[:n_full], packed_weight(w2, False, prec, rows=(1, g_dim + 1)), bs[2][1:], g_dim, 0, 1.0, prec)
+        ctx.cfg = (n, n_full, act, act_param, prec, in_dim, x.shape)
+        if need_grad:
+            ctx.save_for_backward(x2, h0, h1, *ws)
+            ctx.packed_t = (packed_weight(w0, True, prec) if ctx.needs_input_grad[0] else None, packed_weight(w1, True, prec),
+                            packed_weight(w2, True, prec, rows=(1, g_dim + 1)) if n_full > 0 else None)
+        if geo is None:
+            geo = torch.empty((0, g_dim), device=dev, dtype=torch.float32)
+            ctx.mark_non_differentiable(geo)
+        return sdf[:, None], geo
+
+    @staticmethod
+    def backward(ctx, dsdf, dgeo):
+        n, n_full, act, act_param, prec, in_dim, x_shape = ctx.cfg
+        x2, h0, h1, w0, w1, w2 = ctx.saved_tensors
+        p0t, p1t, p2t = ctx.packed_t
+        dev = x2.device
+        hid, g_dim = w1.shape[0], w2.shape[0] - 1
+        d = torch.zeros((n,), device=dev) if dsdf is None else _f(dsdf).reshape(n)
+        dw0, db0 = torch.zeros_like(w0), torch.zeros((w0.shape[0],), device=dev)
+        dw1, db1 = torch.zeros_like(w1), torch.zeros((hid,), device=dev)
+        dw2, db2 = torch.zeros_like(w2), torch.zeros((w2.shape[0],), device=dev)
+        dz0 = torch.empty((n, hid), device=dev, dtype=torch.float32)
+        if n_full > 0:
+            dg = torch.zeros((n_full, g_dim), device=dev) if dgeo is None else _rows(dgeo.reshape(n_full, g_dim), g_dim)
+            h1c, h0c, dc = h1[:n_full], h0[:n_full], d[:n_full]
+            linear_bwd_weight_tc(dg, h1c, dw2[1:], db2[1:], prec)
+            dz1c = torch.empty((n_full, hid), device=dev, dtype=torch.float32)
+            call("mmsb_linear_bwd_data_rank1_tc", ptr(dg), _i64(dg.stride(0)), ptr(p2t), ptr(dz1c), _i64(hid), ptr(h1c),
+                 _i64(hid), _i32(act), _f32(act_param), _i64(n_full), _i32(hid), _i32(g_dim), _i32(prec), ptr(dc), ptr(w2),
+                 stream_ptr())
+            # the head's own weight / bias gradient from the centre rows (one output: the row-streaming SIMT kernel)
+            call("mmsb_linear_bwd_weight", ptr(dc), _i64(1), ptr(h1c), _i64(hid), ptr(dw2), ptr(db2), _i64(n_full), _i32(hid),
+                 _i32(1), stream_ptr())
+            linear_bwd_weight_tc(dz1c, h0c, dw1, db1, prec)
+            linear_bwd_data_tc(dz1c, p1t, hid, h0c, act, act_param, prec, out=dz0[:n_full])
+        if n > n_full:
+            h1t, h0t, dt = h1[n_full:], h0[n_full:], d[n_full:]
+            m = n - n_full
+            call("mmsb_linear_bwd_weight_head_tc", ptr(h1t), _i64(hid), _i32(act), _f32(act_param), ptr(dt), ptr(w2), ptr(h0t),
+                 _i64(hid), ptr(dw1), ptr(db1), ptr(dw2), _i64(m), _i32(hid), _i32(hid), _i32(prec), stream_ptr())
+            db2[0:1] += dt.sum()
+            call("mmsb_linear_bwd_data_head_tc", ptr(h1t), _i64(hid), _i32(act), _f32(act_param), ptr(dt), ptr(w2), ptr(p1t),
+                 ptr(dz0[n_full:]), _i64(hid), ptr(h0t), _i64(hid), _i32(act), _f32(act_param), _i64(m), _i32(hid), _i32(hid),
+                 _i32(prec), stream_ptr())
+        linear_bwd_weight_tc(dz0, x2, dw0, db0, prec)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _padded_rows(n, in_dim, dev)
+            linear_bwd_data_tc(dz0, p0t, in_dim, None, 0, 1.0, prec, out=dx)
+            if tuple(dx.shape) != tuple(x_shape):
+                dx = dx.reshape(x_shape)
+        return dx, None, None, None, dw0, db0, dw1, db1, dw2, db2
+
+
+def sdf_net_forward(x, n_full, weights, biases, act: str, act_param: float):
+    return SdfNetFn.apply(x, int(n_full), ACT[act], float(act_param), weights[0], biases[0], weights[1], biases[1], weights[2],
+                          biases[2])
 
 
 def mlp_forward(x, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]], hidden_act: str,

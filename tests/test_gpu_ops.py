@@ -450,3 +450,35 @@ def test_mlp_precision_modes_agree(prec):
     assert_close(y, h, rtol=tol, what="y")
     for a, r, name in zip(got, ref, ["dx", "dw0", "dw1", "dw2", "db0", "db1", "db2"]):
         assert_close(a, r, rtol=tol, what=name)
+
+
+@pytest.mark.parametrize("n,n_full", [(5000, 1000), (777, 0), (4096, 4096), (130, 1)])
+def test_sdf_net_fused_head_vs_fp64(n, n_full):
+    """ops.SdfNetFn (sdf head fused into layer 1's epilogue / operand producers, geometry features only for the first
+    n_full rows) against the plain three-layer network in fp64: outputs and every gradient."""
+    from multimodalstudio_b200 import ops
+    torch.manual_seed(n + n_full)
+    x = (torch.randn(n, 72, device=DEV)[:, :71] * 0.5).requires_grad_()
+    ws = [(torch.randn(256, 71, device=DEV) * 0.1).requires_grad_(), (torch.randn(256, 256, device=DEV) * 0.06).requires_grad_(),
+          (torch.randn(257, 256, device=DEV) * 0.06).requires_grad_()]
+    bs = [(torch.randn(o, device=DEV) * 0.1).requires_grad_() for o in (256, 256, 257)]
+    sdf, geo = ops.sdf_net_forward(x, n_full, ws, bs, "Softplus", 100.0)
+    h = x.double()
+    for w, b in zip(ws[:2], bs[:2]):
+        h = torch.nn.functional.softplus(h @ w.double().T + b.double(), beta=100)
+    out = h @ ws[2].double().T + bs[2].double()
+    assert_close(sdf, out[:, :1], rtol=2e-5, what="sdf")
+    assert geo.shape == (n_full, 256)
+    g_sdf = torch.randn(n, 1, device=DEV)
+    g_geo = torch.randn(n_full, 256, device=DEV)
+    loss_ref = (out[:, :1] * g_sdf.double()).sum() + (out[:n_full, 1:] * g_geo.double()).sum()
+    loss = (sdf * g_sdf).sum() + ((geo * g_geo).sum() if n_full else 0.0)
+    if n_full:
+        assert_close(geo, out[:n_full, 1:], rtol=2e-5, what="geo")
+    params = [x] + ws + bs
+    ref = torch.autograd.grad(loss_ref, params, allow_unused=True)
+    got = torch.autograd.grad(loss, params, allow_unused=True)
+    for a, r, name in zip(got, ref, ["dx", "dw0", "dw1", "dw2", "db0", "db1", "db2"]):
+        if r is None:
+            r = torch.zeros_like(a)
+        assert_close(a, r, rtol=3e-5, atol=1e-7, what=name)
