@@ -49,6 +49,17 @@ __host__ __device__ constexpr int smem_bytes(int nparts) {
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// Explicit shared-space accesses: the staging pointers are derived from an integer-aligned base, which hides the
+// address space from the compiler (it would emit generic LD / ST: slower path, long-scoreboard latency).
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -132,11 +143,11 @@ template <int NPARTS>
 __device__ __forceinline__ void split_store4(uint8_t* hi, uint8_t* lo, uint32_t off, const float4& v) {
   float4 h;
   h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-  *reinterpret_cast<float4*>(hi + off) = h;
+  sts128(smem_u32(hi) + off, h);
   if (NPARTS == 2) {
     float4 l;
     l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-    *reinterpret_cast<float4*>(lo + off) = l;
+    sts128(smem_u32(lo) + off, l);
   }
 }
 // 16 bytes at (row r, k..k+3) of P[r*ld + k]; zero outside [0,rmax) x [0,kmax)
@@ -312,7 +323,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& e, const float* stg
     const int r = (lane >> 2) + 8 * i;
     const int64_t row = row0 + r;
     if (row >= e.M) continue;
-    float4 x = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * q4);
+    float4 x = lds128(smem_u32(stg + r * STG_LD + 4 * q4));
     float* dst = e.C + row * e.ldc + col;
     if (EPI == EPI_FWD) {
       x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
@@ -353,9 +364,9 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, uint32_t (&v)[C
                                                int64_t row0, int col0, bool vec_ok, float (&hacc)[4]) {
 #pragma unroll
   for (int j = 0; j < CH / 4; ++j)
-    *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) =
-        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                    __uint_as_float(v[4 * j + 3]));
+    sts128(smem_u32(stg + lane * STG_LD + 4 * j),
+           make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                       __uint_as_float(v[4 * j + 3])));
   __syncwarp();
   const int act = EPI == EPI_FWD ? e.act : (EPI == EPI_DGRAD && e.yprev ? e.act_prev : MMSB_ACT_NONE);
   switch (act) {
