@@ -214,6 +214,139 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_kernel(HashGridParams p, con
   }
 }
 
+
+// ---- F = 2 fast path: one thread per (point, group of 4 consecutive levels) ------------------------------------------
+// The 8 floats a thread produces are one 32-byte sector of the point's feature row: full-sector stores (the
+// one-level-per-thread mapping writes 8 of every 32 bytes, which the L2 turns into a read-modify-write of the whole
+// sector from DRAM: 4x write and ~2 GB of fill traffic per 2.6 M look-ups in ncu).  blockIdx.y = level group, so the
+// gathers of the concurrently running blocks stay inside 4 levels (16 MiB) of the table; 32 independent gathers per
+// thread are in flight.
+constexpr int LV = 4;
+
+__global__ void __launch_bounds__(256) hashgrid_fwd4_kernel(HashGridParams p, const float* __restrict__ x, int64_t ldx,
+                                                            const float* __restrict__ table,
+                                                            const float* __restrict__ mask, float* __restrict__ out,
+                                                            int64_t ld_out, int64_t* __restrict__ idx_out, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int level0 = blockIdx.y * LV;
+  if (i >= n) return;
+  const float* xi = x + i * ldx;
+  const float x0 = __ldg(xi), x1 = __ldg(xi + 1), x2 = __ldg(xi + 2);
+  Corner c[LV];
+  Feat<2> f[LV][8];
+#pragma unroll
+  for (int l = 0; l < LV; ++l) {
+    c[l] = corners(p, level0 + l, x0, x1, x2);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[l][k] = load_feat<2>(table, c[l].h[k]);
+  }
+  float r[2 * LV];
+#pragma unroll
+  for (int l = 0; l < LV; ++l) {
+    const int level = level0 + l;
+    if (idx_out) {
+      int64_t* io = idx_out + (i * p.L + level) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) io[k] = int64_t(c[l].h[k]);
+    }
+    const float ox = c[l].o[0], oy = c[l].o[1], oz = c[l].o[2];
+    const float mx = __fsub_rn(1.f, ox), my = __fsub_rn(1.f, oy), mz = __fsub_rn(1.f, oz);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      // ref: encodings.py:292-302
+      const float f03 = lerp_ref(f[l][0].v[j], f[l][3].v[j], ox, mx);
+      const float f12 = lerp_ref(f[l][1].v[j], f[l][2].v[j], ox, mx);
+      const float f56 = lerp_ref(f[l][5].v[j], f[l][6].v[j], ox, mx);
+      const float f47 = lerp_ref(f[l][4].v[j], f[l][7].v[j], ox, mx);
+      const float f0312 = lerp_ref(f03, f12, oy, my);
+      const float f4756 = lerp_ref(f47, f56, oy, my);
+      float v = lerp_ref(f0312, f4756, oz, mz);
+      if (mask) v = __fmul_rn(v, __ldg(mask + level * 2 + j));
+      r[2 * l + j] = v;
+    }
+  }
+  float* o = out + i * ld_out + level0 * 2;
+  if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+    reinterpret_cast<float4*>(o)[0] = make_float4(r[0], r[1], r[2], r[3]);
+    reinterpret_cast<float4*>(o)[1] = make_float4(r[4], r[5], r[6], r[7]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 2 * LV; ++j) o[j] = r[j];
+  }
+}
+
+__global__ void __launch_bounds__(256) hashgrid_bwd4_kernel(HashGridParams p, const float* __restrict__ x, int64_t ldx,
+                                                            const float* __restrict__ table,
+                                                            const float* __restrict__ mask,
+                                                            const float* __restrict__ dout, int64_t ld_dout,
+                                                            float* __restrict__ dtable, float* __restrict__ dx,
+                                                            int64_t lddx, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int level0 = blockIdx.y * LV;
+  if (i >= n) return;
+  const float* xi = x + i * ldx;
+  const float x0 = __ldg(xi), x1 = __ldg(xi + 1), x2 = __ldg(xi + 2);
+  float g[2 * LV];
+  const float* gi = dout + i * ld_dout + level0 * 2;
+  if ((reinterpret_cast<uintptr_t>(gi) & 15) == 0) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(gi)), b = __ldg(reinterpret_cast<const float4*>(gi) + 1);
+    g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 2 * LV; ++j) g[j] = __ldg(gi + j);
+  }
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+  for (int l = 0; l < LV; ++l) {
+    const int level = level0 + l;
+    float gl[2] = {g[2 * l], g[2 * l + 1]};
+    if (mask) {
+      gl[0] *= __ldg(mask + level * 2);
+      gl[1] *= __ldg(mask + level * 2 + 1);
+    }
+    if (gl[0] == 0.f && gl[1] == 0.f) continue;   // masked (coarse-to-fine) levels contribute exact zeros
+    const Corner c = corners(p, level, x0, x1, x2);
+    const float ox = c.o[0], oy = c.o[1], oz = c.o[2];
+    const float mx = 1.f - ox, my = 1.f - oy, mz = 1.f - oz;
+    if (dtable) {
+      atomic_add_feat<2>(dtable, c.h[0], gl, ox * oy * oz);
+      atomic_add_feat<2>(dtable, c.h[1], gl, ox * my * oz);
+      atomic_add_feat<2>(dtable, c.h[2], gl, mx * my * oz);
+      atomic_add_feat<2>(dtable, c.h[3], gl, mx * oy * oz);
+      atomic_add_feat<2>(dtable, c.h[4], gl, ox * oy * mz);
+      atomic_add_feat<2>(dtable, c.h[5], gl, ox * my * mz);
+      atomic_add_feat<2>(dtable, c.h[6], gl, mx * my * mz);
+      atomic_add_feat<2>(dtable, c.h[7], gl, mx * oy * mz);
+    }
+    if (dx) {
+      Feat<2> f[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = load_feat<2>(table, c.h[k]);
+      float lx = 0.f, ly = 0.f, lz = 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float f03 = f[0].v[j] * ox + f[3].v[j] * mx, d03 = f[0].v[j] - f[3].v[j];
+        const float f12 = f[1].v[j] * ox + f[2].v[j] * mx, d12 = f[1].v[j] - f[2].v[j];
+        const float f56 = f[5].v[j] * ox + f[6].v[j] * mx, d56 = f[5].v[j] - f[6].v[j];
+        const float f47 = f[4].v[j] * ox + f[7].v[j] * mx, d47 = f[4].v[j] - f[7].v[j];
+        const float f0312 = f03 * oy + f12 * my, f4756 = f47 * oy + f56 * my;
+        lx += gl[j] * ((d03 * oy + d12 * my) * oz + (d47 * oy + d56 * my) * mz);
+        ly += gl[j] * ((f03 - f12) * oz + (f47 - f56) * mz);
+        lz += gl[j] * (f0312 - f4756);
+      }
+      float sc = c.res;
+      if (p.radius > 0.f) sc /= (2.f * p.radius);
+      gx += lx * c.d[0] * sc; gy += ly * c.d[1] * sc; gz += lz * c.d[2] * sc;
+    }
+  }
+  if (dx) {
+    float* d = dx + i * lddx;
+    atomicAdd(d + 0, gx);
+    atomicAdd(d + 1, gy);
+    atomicAdd(d + 2, gz);
+  }
+}
+
 static int make_params(const MmsbHashGridDesc* d, HashGridParams& p) {
   MMSB_REQUIRE(d != nullptr, "hashgrid: desc is NULL");
   MMSB_REQUIRE(d->num_levels >= 1 && d->num_levels <= MMSB_MAX_LEVELS, "hashgrid: num_levels %d not in [1,%d]",
@@ -246,6 +379,11 @@ extern "C" int mmsb_hashgrid_fwd(const MmsbHashGridDesc* desc, const float* x, i
   MMSB_REQUIRE(x && table && out, "hashgrid_fwd: NULL pointer");
   dim3 grid((unsigned)ceil_div(n, 256), p.L), block(256);
   cudaStream_t s = as_stream(stream);
+  if (desc->features_per_level == 2 && p.L % LV == 0) {
+    grid.y = p.L / LV;
+    hashgrid_fwd4_kernel<<<grid, block, 0, s>>>(p, x, ldx, table, mask, out, ld_out, idx_out, n);
+    return check_launch("hashgrid_fwd");
+  }
   switch (desc->features_per_level) {
     case 1: hashgrid_fwd_kernel<1><<<grid, block, 0, s>>>(p, x, ldx, table, mask, out, ld_out, idx_out, n); break;
     case 2: hashgrid_fwd_kernel<2><<<grid, block, 0, s>>>(p, x, ldx, table, mask, out, ld_out, idx_out, n); break;
@@ -276,6 +414,11 @@ extern "C" int mmsb_hashgrid_bwd(const MmsbHashGridDesc* desc, const float* x, i
     }
   }
   dim3 grid((unsigned)ceil_div(n, 256), p.L), block(256);
+  if (desc->features_per_level == 2 && p.L % LV == 0) {
+    grid.y = p.L / LV;
+    hashgrid_bwd4_kernel<<<grid, block, 0, s>>>(p, x, ldx, table, mask, dout, ld_dout, dtable, dx, lddx, n);
+    return check_launch("hashgrid_bwd");
+  }
   switch (desc->features_per_level) {
     case 1: hashgrid_bwd_kernel<1><<<grid, block, 0, s>>>(p, x, ldx, table, mask, dout, ld_dout, dtable, dx, lddx, n); break;
     case 2: hashgrid_bwd_kernel<2><<<grid, block, 0, s>>>(p, x, ldx, table, mask, dout, ld_dout, dtable, dx, lddx, n); break;

@@ -231,7 +231,8 @@ class MLP(FieldComponent):
             self.weight_norm()
         self.act_param = float(self.config.activation_params.get("beta", 1.0)) if self.config.activation == "Softplus" else 1.0
 
-    def forward(self, input_tensor, n_out_used: Optional[int] = None):
+    def forward(self, input_tensor, n_out_used: Optional[int] = None, first_weight=None):
+        """`first_weight`: replaces layers[0].weight (a column-permuted view of it for reordered input rows)."""
         out_act = self.config.out_activation
         if out_act == "Softplus" and self.config.activation != "Softplus":
             # nn.Softplus() default beta for the output (density head) while hidden is ReLU: one act_param suffices
@@ -239,6 +240,8 @@ class MLP(FieldComponent):
         else:
             act_param = self.act_param
         weights = [layer.weight for layer in self.layers]
+        if first_weight is not None:
+            weights[0] = first_weight
         biases = [layer.bias for layer in self.layers]
         return ops.mlp_forward(input_tensor, weights, biases, self.config.activation, out_act, act_param,
                                tuple(self.config.skip_connections), n_out_used)
@@ -366,8 +369,9 @@ class FeatureGridAndMLP(FieldComponent):
         """`pieces` + `positions`: the row cat[pieces..., hash features(positions)] is assembled in place by the
         encoder kernels (ops.assemble) instead of torch.cat over materialised parts — same values."""
         if pieces is not None and not self.config.return_features:
-            mlp_input = ops.assemble(list(pieces) + [self.feature_grid.piece(positions)])
-            return self.mlp_head(mlp_input, n_out_used=n_out_used)
+            mlp_input, perm = self.assemble_input(pieces, positions)
+            w0 = ops.permuted_columns(self.mlp_head.layers[0].weight, perm)
+            return self.mlp_head(mlp_input, n_out_used=n_out_used, first_weight=w0)
         if input_tensor is None:
             input_tensor = ops.assemble(list(pieces))
         features = self.feature_grid(input_tensor[..., :3])
@@ -376,6 +380,18 @@ class FeatureGridAndMLP(FieldComponent):
         if self.config.return_features:
             return output, features
         return output
+
+    def assemble_input(self, pieces, positions):
+        """The MLP input row with the hash features FIRST and the other pieces by decreasing width (the hash-grid and
+        copy kernels then write 16/32-byte aligned), plus the column permutation (new position -> reference column of
+        cat[pieces..., features], feature_structures.py:164) to apply to the first layer's weight."""
+        all_pieces = list(pieces) + [self.feature_grid.piece(positions)]
+        widths = [ops._piece_width(p) for p in all_pieces]
+        starts = [sum(widths[:i]) for i in range(len(widths))]
+        last = len(all_pieces) - 1
+        order = [last] + sorted(range(last), key=lambda i: -widths[i])
+        perm = tuple(c for i in order for c in range(starts[i], starts[i] + widths[i]))
+        return ops.assemble([all_pieces[i] for i in order]), perm
 
     def get_training_callbacks(self, training_callback_attributes):
         return self.feature_grid.get_training_callbacks(training_callback_attributes)

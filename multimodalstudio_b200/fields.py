@@ -66,9 +66,10 @@ class SDFField(SurfaceField):
         """x [n, 3] -> sdf [n, 1] for every row, geo_feature [n_full, G] for the first n_full rows (one network call for
         the centre evaluations and the finite-difference taps of surface_model.py:129-152)."""
         mlp = self.field.mlp_head
-        rows = ops.assemble([self.position_encoding.piece(x), self.field.feature_grid.piece(x)])
-        return ops.sdf_net_forward(rows, n_full, [l.weight for l in mlp.layers], [l.bias for l in mlp.layers],
-                                   mlp.config.activation, mlp.act_param)
+        rows, perm = self.field.assemble_input([self.position_encoding.piece(x)], x)
+        weights = [l.weight for l in mlp.layers]
+        weights[0] = ops.permuted_columns(weights[0], perm)
+        return ops.sdf_net_forward(rows, n_full, weights, [l.bias for l in mlp.layers], mlp.config.activation, mlp.act_param)
 
     def forward(self, x, sdf_only: bool = False):
         if self._fused():

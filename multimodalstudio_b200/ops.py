@@ -415,6 +415,27 @@ def set_mlp_precision(precision: int) -> None:
 def clear_pack_cache() -> None:
     """Call after every optimiser step (the packed operands are functions of the weights)."""
     _PACK_CACHE.clear()
+    _PERM_CACHE.clear()
+
+
+_PERM_CACHE = {}
+
+
+def permuted_columns(w, perm):
+    """w[:, perm] (perm: tuple of old column indices in the new order), memoised like packed_weight so that the packed
+    operands of the permuted weight are reused within a step.  The MLP input rows are assembled with the hash features
+    first (sector-aligned stores of the hash-grid kernel); the first layer's weight follows with this column gather,
+    whose autograd backward scatters the gradient back to the reference's column order."""
+    key = (id(w), perm)
+    hit = _PERM_CACHE.get(key)
+    if hit is not None and hit[0]() is w and hit[1] == w._version and hit[2].requires_grad == (w.requires_grad and torch.is_grad_enabled()):
+        return hit[2]
+    idx = const_tensor(("perm", perm), lambda: torch.tensor(perm, dtype=torch.long), w.device)
+    out = w.index_select(1, idx)
+    if len(_PERM_CACHE) > 128:
+        _PERM_CACHE.clear()
+    _PERM_CACHE[key] = (weakref.ref(w), w._version, out)
+    return out
 
 
 def _use_tc(w) -> bool:
