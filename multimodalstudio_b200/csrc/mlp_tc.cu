@@ -246,6 +246,7 @@ enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_ATOMIC = 2 };
 
 struct EpiArgs {
   float* C; int64_t ldc; int64_t M; int N;   // logical extents of C
+  int64_t cs;                                // column stride of C for the reducing epilogue (0 = 1; != 1: transposed store)
   const float* bias; int act; float act_param;
   const float* yprev; int64_t ld_yprev; int act_prev; float act_prev_param;
   // forward with a fused one-output head: head_out[row] += sum_col act(z)[row, col] * head_w[col] (+ head_b once);
@@ -343,10 +344,12 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& e, const float* stg
       }
     }
     if (EPI == EPI_ATOMIC) {
+      const int64_t cs = e.cs ? e.cs : 1;
+      dst = e.C + row * e.ldc + col * cs;
       atomicAdd(dst, x.x);
-      if (col + 1 < e.N) atomicAdd(dst + 1, x.y);
-      if (col + 2 < e.N) atomicAdd(dst + 2, x.z);
-      if (col + 3 < e.N) atomicAdd(dst + 3, x.w);
+      if (col + 1 < e.N) atomicAdd(dst + cs, x.y);
+      if (col + 2 < e.N) atomicAdd(dst + 2 * cs, x.z);
+      if (col + 3 < e.N) atomicAdd(dst + 3 * cs, x.w);
     } else if (vec_ok && full) {
       *reinterpret_cast<float4*>(dst) = x;
     } else {
@@ -654,6 +657,11 @@ struct WgradArgs {
   // generated dz (weight gradient below a fused head): dz[r, c] = hd[r] * hw[c] * act'(dz_mem[r, c]) with dz_mem = the
   // stored activations y of the layer; dhw[c] += sum_r hd[r] * y[r, c] (the head's own weight gradient)
   const float* hd; const float* hw; int hact; float hact_param; float* dhw;
+  // transposed: the kernel computes dW^T = x^T dz (the fields above then hold: dz/lddz/out_dim = x and its width,
+  // x/ldx/in_dim = dz and its width): used when in_dim <= 128 < out_dim so that the accumulator is 128 x 256 instead
+  // of two 128 x 80 ones (a k-block of MMAs long enough to hide the staging hand-shake); the bias gradient is then
+  // summed on the B side and the tile is reduced into dw with column stride lddw.
+  int transposed;
 };
 
 template <int NPARTS>
@@ -709,8 +717,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
       const bool vec_a = ((g.lddz & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.dz) & 15) == 0);
       const bool vec_b = ((g.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.x) & 15) == 0);
       const bool b_active = cb < cpr;
-      const bool want_db = g.db != nullptr && nt == 0;
-      float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f), hsum = colsum;
+      const bool want_db = g.db != nullptr && nt == 0 && !g.transposed;
+      const bool want_db_b = g.db != nullptr && mt == 0 && g.transposed && b_active;
+      float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f), hsum = colsum, bsum = colsum;
       float4 va[4], vb[8];
       float hd[4];
       const float4 hw4 = g.hd && m0 + ca * 4 < g.out_dim ? load_cols4(g.hw, m0 + ca * 4, g.out_dim) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -750,7 +759,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
         }
         if (b_active) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) split_store4<NPARTS>(b_hi, b_hi + b_part, mn_offset(cb, kbb + 4 * i), vb[i]);
+          for (int i = 0; i < 8; ++i) {
+            split_store4<NPARTS>(b_hi, b_hi + b_part, mn_offset(cb, kbb + 4 * i), vb[i]);
+            bsum.x += vb[i].x; bsum.y += vb[i].y; bsum.z += vb[i].z; bsum.w += vb[i].w;
+          }
         }
         fence_async_smem();
         __syncwarp();
@@ -766,6 +778,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
         if (col + 2 < g.out_dim) atomicAdd(g.db + col + 2, colsum.z);
         if (col + 3 < g.out_dim) atomicAdd(g.db + col + 3, colsum.w);
       }
+      if (want_db_b) {
+        const int col = n0 + cb * 4;
+        if (col < g.in_dim) atomicAdd(g.db + col, bsum.x);
+        if (col + 1 < g.in_dim) atomicAdd(g.db + col + 1, bsum.y);
+        if (col + 2 < g.in_dim) atomicAdd(g.db + col + 2, bsum.z);
+        if (col + 3 < g.in_dim) atomicAdd(g.db + col + 3, bsum.w);
+      }
       if (g.hd && g.dhw && nt == 0) {
         const int col = m0 + ca * 4;
         if (col < g.out_dim) atomicAdd(g.dhw + col, hsum.x);
@@ -778,6 +797,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
         float* stg = stg_all + warp * 32 * STG_LD;
         EpiArgs e{};
         e.C = g.dw; e.ldc = g.lddw; e.M = g.out_dim; e.N = g.in_dim;
+        if (g.transposed) { e.ldc = 1; e.cs = g.lddw; }
         mbar_wait(bar_tfull, 0);
         tc_fence_after();
         YPrev y_none;
@@ -918,8 +938,12 @@ static int rows_wgrad(const float* dz, int64_t lddz, const float* x, int64_t ldx
   g.dz = dz; g.lddz = lddz; g.out_dim = out_dim; g.x = x; g.ldx = ldx; g.in_dim = in_dim;
   g.dw = dw; g.lddw = in_dim; g.db = db; g.rows = n;
   g.hd = hd; g.hw = hw; g.hact = hact; g.hact_param = hact_param; g.dhw = dhw;
-  const int m_tiles = int(ceil_div(out_dim, tc::TM));
-  g.n_tiles = int(ceil_div(tc::pad16(in_dim), tc::NT));
+  if (hd == nullptr && in_dim <= tc::TM && out_dim > tc::TM) {
+    g.transposed = 1;
+    g.dz = x; g.lddz = ldx; g.out_dim = in_dim; g.x = dz; g.ldx = lddz; g.in_dim = out_dim;
+  }
+  const int m_tiles = int(ceil_div(g.out_dim, tc::TM));
+  g.n_tiles = int(ceil_div(tc::pad16(g.in_dim), tc::NT));
   const int tiles = m_tiles * g.n_tiles;
   int64_t splits = kNumSMs / tiles;
   if (splits < 1) splits = 1;

@@ -506,12 +506,13 @@ class RadianceModel(nn.Module):
         up_directions = ray_samples.frustums.up_directions.expand(*shape, 3).reshape(-1, 3)
         if bounds is not None:
             s_ = shape[-1]
-            for mod, (a, b) in bounds.items():
+            # torch.split: ONE cat in backward (per-modality indexing would zero-fill and add a full-size gradient each)
+            feats = torch.split(radiance_feature, [(b - a) * s_ for a, b in bounds.values()], dim=0)
+            for (mod, (a, b)), feat in zip(bounds.items(), feats):
                 rows = slice(a * s_, b * s_)
                 outputs[mod] = {}
                 for head in (heads[mod] if heads is not None else self.modalities):
-                    out = self.modality_heads[head](radiance_feature[rows], directions=directions[rows],
-                                                    up_directions=up_directions[rows])
+                    out = self.modality_heads[head](feat, directions=directions[rows], up_directions=up_directions[rows])
                     outputs[mod][head] = out.view(b - a, s_, -1)
             return outputs
         for mod in (heads if heads is not None else self.modalities):
@@ -568,13 +569,14 @@ class BackgroundModel(nn.Module):
         up_directions = ray_samples.frustums.up_directions.expand(*shape, 3).reshape(-1, 3)
         if bounds is not None:
             s_ = shape[-1]
-            for mod, (a, b) in bounds.items():
+            feats = torch.split(radiance_feature, [(b - a) * s_ for a, b in bounds.values()], dim=0)
+            wsplit = torch.split(weights[..., 0], [b - a for a, b in bounds.values()], dim=0)
+            for (mod, (a, b)), feat, w in zip(bounds.items(), feats, wsplit):
                 rows = slice(a * s_, b * s_)
                 outputs[mod] = {}
                 for head in (heads[mod] if heads is not None else self.modalities):
-                    radiance = self.modality_heads[head](radiance_feature[rows], directions=directions[rows],
-                                                         up_directions=up_directions[rows])
-                    outputs[mod][head] = ops.CompositeFn.apply(weights[a:b, :, 0], radiance.view(b - a, s_, -1), None)
+                    radiance = self.modality_heads[head](feat, directions=directions[rows], up_directions=up_directions[rows])
+                    outputs[mod][head] = ops.CompositeFn.apply(w, radiance.view(b - a, s_, -1), None)
             return outputs
         for mod in (heads if heads is not None else self.modalities):
             radiance = self.modality_heads[mod](radiance_feature, directions=directions, up_directions=up_directions)

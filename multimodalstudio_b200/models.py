@@ -148,15 +148,19 @@ class BaseModel(torch.nn.Module):
         radiance = self.radiance_model(ray_samples=samples, normals=geometry["normals"].detach(),
                                        geo_feature=geometry["geo_feature"], heads=heads, bounds=bounds)
         outputs = {m: None for m in ray_bundles}
-        for m in mods:
+        # torch.split: one cat in backward instead of a zero-filled full-size gradient (+ add) per modality
+        sizes = [bounds[m][1] - bounds[m][0] for m in mods]
+        split = {k: torch.split(geometry[k], sizes, dim=0) if geometry.get(k) is not None else None
+                 for k in ("weights", "normals", "gradients", "hessians")}
+        for i, m in enumerate(mods):
             a, b = bounds[m]
             renderer_input = dict(radiance[m])
-            renderer_input.update({"normals": geometry["normals"][a:b], "depth": samples.slice_rays(a, b),
+            renderer_input.update({"normals": split["normals"][i], "depth": samples.slice_rays(a, b),
                                    "background": background[m] if background is not None else None})
-            out = self.renderer.render(geometry["weights"][a:b], renderer_input, mask[a:b] if mask is not None else None)
+            out = self.renderer.render(split["weights"][i], renderer_input, mask[a:b] if mask is not None else None)
             if self.training:
-                out.update({"gradients": geometry["gradients"][a:b],
-                            "hessians": geometry["hessians"][a:b] if geometry["hessians"] is not None else None,
+                out.update({"gradients": split["gradients"][i],
+                            "hessians": split["hessians"][i] if split["hessians"] is not None else None,
                             "inv_s": geometry["inv_s"], "ray_mask": mask[a:b] if mask is not None else None})
             outputs[m] = out
         return outputs

@@ -54,6 +54,18 @@ def _rows(t: torch.Tensor, last: int) -> torch.Tensor:
     return _f(t).reshape(-1, last)
 
 
+def _zeros_many(shapes, device):
+    """Zero-initialised fp32 tensors of the given shapes carved out of ONE buffer (one fill kernel instead of one per
+    gradient accumulator; every tensor starts on a 16-byte boundary)."""
+    sizes = [int(np.prod(sh)) if len(sh) else 1 for sh in shapes]
+    offs, total = [], 0
+    for k in sizes:
+        offs.append(total)
+        total += (k + 3) // 4 * 4
+    flat = torch.zeros((total,), device=device, dtype=torch.float32)
+    return [flat[o:o + k].view(sh) for o, k, sh in zip(offs, sizes, shapes)]
+
+
 def _padded_rows(n: int, cols: int, device) -> torch.Tensor:
     """[n, cols] fp32 view whose rows start on 16-byte boundaries (leading dimension rounded up to 4 floats)."""
     ld = (cols + 3) // 4 * 4
@@ -523,14 +535,23 @@ class MLPFn(torch.autograd.Function):
         grads = [None] * (2 * nl)
         dx_skip = None
         need_dx = ctx.needs_input_grad[0]
+        want = [ctx.needs_input_grad[6 + 2 * i] or (has[2 * i + 1] and ctx.needs_input_grad[7 + 2 * i]) for i in range(nl)]
+        shapes = []
+        for i in range(nl):
+            if want[i]:
+                shapes += [tuple(ws[i].shape)] + ([(ws[i].shape[0],)] if has[2 * i + 1] else [])
+        bufs = iter(_zeros_many(shapes, ws[0].device)) if shapes else iter(())
+        acc = {}
+        for i in range(nl):
+            if want[i]:
+                acc[i] = (next(bufs), next(bufs) if has[2 * i + 1] else None)
         for i in range(nl - 1, -1, -1):
             w = ws[i]
             o, k = w.shape
             xin = acts[i]
             tc = prec != 0 and _use_tc(w)
-            if ctx.needs_input_grad[6 + 2 * i] or (has[2 * i + 1] and ctx.needs_input_grad[7 + 2 * i]):
-                dw = torch.zeros((o, k), device=w.device, dtype=torch.float32)
-                db = torch.zeros((o,), device=w.device, dtype=torch.float32) if has[2 * i + 1] else None
+            if want[i]:
+                dw, db = acc[i]
                 if tc:
                     linear_bwd_weight_tc(dz, xin, dw, db, prec)
                 else:
@@ -630,9 +651,8 @@ class SdfNetFn(torch.autograd.Function):
         dev = x2.device
         hid, g_dim = w1.shape[0], w2.shape[0] - 1
         d = torch.zeros((n,), device=dev) if dsdf is None else _f(dsdf).reshape(n)
-        dw0, db0 = torch.zeros_like(w0), torch.zeros((w0.shape[0],), device=dev)
-        dw1, db1 = torch.zeros_like(w1), torch.zeros((hid,), device=dev)
-        dw2, db2 = torch.zeros_like(w2), torch.zeros((w2.shape[0],), device=dev)
+        dw0, db0, dw1, db1, dw2, db2 = _zeros_many([tuple(w0.shape), (w0.shape[0],), tuple(w1.shape), (hid,), tuple(w2.shape),
+                                                    (w2.shape[0],)], dev)
         dz0 = torch.empty((n, hid), device=dev, dtype=torch.float32)
         if n_full > 0:
             dg = torch.zeros((n_full, g_dim), device=dev) if dgeo is None else _rows(dgeo.reshape(n_full, g_dim), g_dim)

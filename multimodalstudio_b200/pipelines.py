@@ -102,11 +102,13 @@ class FlatAdamW:
         self.exp_avg = torch.zeros(n, device=dev)
         self.exp_avg_sq = torch.zeros(n, device=dev)
         off = 0
+        self.grad_views = []
         for p in self.params:
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p)
-            p.grad = self.grad[off:off + k].view_as(p)
+            self.grad_views.append(self.grad[off:off + k].view_as(p))
+            p.grad = self.grad_views[-1]
             off += (k + align - 1) // align * align
         self.lr, self.wd, self.eps, self.betas, self.max_norm = lr, weight_decay, eps, betas, max_norm
         self.step_count = 0
@@ -118,6 +120,27 @@ class FlatAdamW:
 
     def zero_grad(self):
         self.grad.zero_()
+        for p, g in zip(self.params, self.grad_views):
+            p.grad = g
+
+    def detach_grads(self):
+        """Before backward: autograd then *assigns* each parameter's gradient instead of launching one in-place add
+        per parameter into the flat buffer."""
+        for p in self.params:
+            p.grad = None
+
+    def gather_grads(self):
+        """After backward: one memset + one multi-tensor copy bring the gradients into the flat buffer (the layout the
+        clip, AdamW and the NCCL all-reduce work on)."""
+        self.grad.zero_()
+        src, dst = [], []
+        for p, g in zip(self.params, self.grad_views):
+            if p.grad is not None:
+                src.append(p.grad)
+                dst.append(g)
+            p.grad = g
+        if src:
+            torch._foreach_copy_(dst, src)
 
     def step(self, lr_factor: float = 1.0):
         self.step_count += 1
@@ -203,8 +226,10 @@ class RawPipeline:
             outputs = self.model(ray_bundles)
         losses, total = self.loss_manager.compute_loss(outputs, targets, coords, step, mosaick_patterns=self.patterns)
         for opt in self.optimizers.values():
-            opt.zero_grad()
+            opt.detach_grads()
         total.backward()
+        for opt in self.optimizers.values():
+            opt.gather_grads()
         # detached: a caller holding on to the losses must not keep the autograd graph (and its AccumulateGrad
         # nodes, which remember the stream they were created on) alive into the next step / a graph capture
         return {k: (v.detach() if torch.is_tensor(v) else v) for k, v in losses.items()}, total.detach()
