@@ -247,6 +247,8 @@ enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_ATOMIC = 2 };
 struct EpiArgs {
   float* C; int64_t ldc; int64_t M; int N;   // logical extents of C
   int64_t cs;                                // column stride of C for the reducing epilogue (0 = 1; != 1: transposed store)
+  int direct;                                // forward: store from the TMEM register layout (lane = row) without the
+                                             // shared-memory transpose (needs 16-byte aligned rows of C)
   const float* bias; int act; float act_param;
   const float* yprev; int64_t ld_yprev; int act_prev; float act_prev_param;
   // forward with a fused one-output head: head_out[row] += sum_col act(z)[row, col] * head_w[col] (+ head_b once);
@@ -361,10 +363,51 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& e, const float* stg
   }
 }
 
+// Forward chunk without the transpose: the lane keeps its row's CH consecutive columns (64 contiguous bytes) and
+// stores them itself.  The two 16-byte halves of a 32-byte sector come from consecutive instructions of the same
+// lane, so they meet in the L2; no shared-memory traffic, no warp synchronisation.
+template <int ACT>
+__device__ __forceinline__ void epilogue_chunk_direct(const EpiArgs& e, uint32_t (&v)[CH], int lane, int64_t row0, int col0,
+                                                      float (&hacc)[4]) {
+  const int64_t row = row0 + lane;
+#pragma unroll
+  for (int j = 0; j < CH / 4; ++j) {
+    const int col = col0 + 4 * j;
+    if (col >= e.N) break;
+    const float4 b4 = load_cols4(e.bias, col, e.N);
+    float4 x = make_float4(__uint_as_float(v[4 * j]) + b4.x, __uint_as_float(v[4 * j + 1]) + b4.y,
+                           __uint_as_float(v[4 * j + 2]) + b4.z, __uint_as_float(v[4 * j + 3]) + b4.w);
+    x = act_fwd4<ACT>(x, e.act_param);
+    if (e.head_w) {
+      const float4 h4 = load_cols4(e.head_w, col, e.N);
+      hacc[0] = fmaf(x.x, h4.x, fmaf(x.y, h4.y, fmaf(x.z, h4.z, fmaf(x.w, h4.w, hacc[0]))));
+    }
+    if (e.C != nullptr && row < e.M) {
+      float* dst = e.C + row * e.ldc + col;
+      if (col + 3 < e.N) {
+        *reinterpret_cast<float4*>(dst) = x;
+      } else {
+        dst[0] = x.x;
+        if (col + 1 < e.N) dst[1] = x.y;
+        if (col + 2 < e.N) dst[2] = x.z;
+      }
+    }
+  }
+}
+
 // One chunk: lane owns row (row0 + lane) in registers -> transpose buffer -> epilogue_rows.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, uint32_t (&v)[CH], float* stg, const YPrev& yp, int lane,
                                                int64_t row0, int col0, bool vec_ok, float (&hacc)[4]) {
+  if (EPI == EPI_FWD && e.direct) {
+    switch (e.act) {
+      case MMSB_ACT_RELU: epilogue_chunk_direct<MMSB_ACT_RELU>(e, v, lane, row0, col0, hacc); break;
+      case MMSB_ACT_SOFTPLUS: epilogue_chunk_direct<MMSB_ACT_SOFTPLUS>(e, v, lane, row0, col0, hacc); break;
+      case MMSB_ACT_SIGMOID: epilogue_chunk_direct<MMSB_ACT_SIGMOID>(e, v, lane, row0, col0, hacc); break;
+      default: epilogue_chunk_direct<MMSB_ACT_NONE>(e, v, lane, row0, col0, hacc); break;
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < CH / 4; ++j)
     sts128(smem_u32(stg + lane * STG_LD + 4 * j),
@@ -396,6 +439,11 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
   // (two warps per row -> two commutative additions onto the caller's zeros: order-independent)
   auto head_flush = [&]() {
     if (EPI != EPI_FWD || e.head_w == nullptr) return;
+    if (e.direct) {   // the lane owns one row
+      const int64_t row = row0 + lane;
+      if (row < e.M) atomicAdd(e.head_out + row, hacc[0] + ((first == 0 && col_base == 0 && e.head_b) ? __ldg(e.head_b) : 0.f));
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float v = hacc[i];
@@ -910,6 +958,11 @@ static int rows_fwd(const float* x, int64_t ldx, const float* packed_w, const fl
   g.A = x; g.lda = ldx; g.M = n; g.K = in_dim; g.Bp = packed_w; g.N = out_dim;
   g.epi.C = y; g.epi.ldc = ldy; g.epi.M = n; g.epi.N = out_dim; g.epi.bias = b; g.epi.act = act; g.epi.act_param = act_param;
   g.epi.head_w = head_w; g.epi.head_b = head_b; g.epi.head_out = head_out;
+  {
+    static int direct = -1;
+    if (direct < 0) { const char* e = getenv("MMSB_TC_DIRECT"); direct = e ? atoi(e) : 0; }   // measured slower than the staged transpose (uncoalesced 16-byte stores): off by default
+    g.epi.direct = direct && (y == nullptr || ((ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0));
+  }
   g.n_tiles = int(ceil_div(tc::pad16(out_dim), tc::NT)); g.nkb = int(ceil_div(in_dim, tc::TK));
   g.total_tiles = ceil_div(n, tc::TM) * g.n_tiles;
   { const char* e = getenv("MMSB_TC_DEBUG"); g.dbg = e ? atoi(e) : 0; }

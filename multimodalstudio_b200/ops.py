@@ -662,9 +662,8 @@ class SdfNetFn(torch.autograd.Function):
             call("mmsb_linear_bwd_data_rank1_tc", ptr(dg), _i64(dg.stride(0)), ptr(p2t), ptr(dz1c), _i64(hid), ptr(h1c),
                  _i64(hid), _i32(act), _f32(act_param), _i64(n_full), _i32(hid), _i32(g_dim), _i32(prec), ptr(dc), ptr(w2),
                  stream_ptr())
-            # the head's own weight / bias gradient from the centre rows (one output: the row-streaming SIMT kernel)
-            call("mmsb_linear_bwd_weight", ptr(dc), _i64(1), ptr(h1c), _i64(hid), ptr(dw2), ptr(db2), _i64(n_full), _i32(hid),
-                 _i32(1), stream_ptr())
+            # the head's own weight / bias gradient from the centre rows (a one-row product)
+            linear_bwd_weight_tc(dc[:, None], h1c, dw2[0:1], db2[0:1], prec)
             linear_bwd_weight_tc(dz1c, h0c, dw1, db1, prec)
             linear_bwd_data_tc(dz1c, p1t, hid, h0c, act, act_param, prec, out=dz0[:n_full])
         if n > n_full:
