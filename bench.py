@@ -250,20 +250,23 @@ def main():
     torch.cuda.synchronize()
     if rank == 0:
         rec = _lib.stop_kernel_timing()
-        flops = {"mmsb_linear_fwd": 0.0, "mmsb_linear_bwd_data": 0.0, "mmsb_linear_bwd_weight": 0.0}
-        msk = {k: 0.0 for k in flops}
-        cnt = {k: 0 for k in flops}
-        hb = {"mmsb_hashgrid_fwd": [0.0, 0.0, 0], "mmsb_hashgrid_bwd": [0.0, 0.0, 0]}
+        # entry point -> (product class, index of n in the argument list; in_dim and out_dim follow it)
+        LAYER = {"mmsb_linear_fwd": ("fwd", 6), "mmsb_linear_fwd_tc": ("fwd", 6), "mmsb_linear_fwd_head_tc": ("fwd", 6),
+                 "mmsb_linear_bwd_data": ("dgrad", 9), "mmsb_linear_bwd_data_tc": ("dgrad", 9),
+                 "mmsb_linear_bwd_data_rank1_tc": ("dgrad", 9), "mmsb_linear_bwd_data_head_tc": ("dgrad", 13),
+                 "mmsb_linear_bwd_weight": ("wgrad", 6), "mmsb_linear_bwd_weight_tc": ("wgrad", 6),
+                 "mmsb_linear_bwd_weight_head_tc": ("wgrad", 11)}
+        KERNEL = {"fwd": "tc_rows_kernel<.,FWD> (mmsb_linear_fwd[_head]_tc)", "dgrad": "tc_rows_kernel<.,DGRAD> (mmsb_linear_bwd_data[_head|_rank1]_tc)",
+                  "wgrad": "tc_wgrad_kernel (mmsb_linear_bwd_weight[_head]_tc)"}
         tc_ms = 0.0
         if os.environ.get("MMSB_BENCH_TABLE"):
             # per entry point and layer shape: calls, total ms over the two instrumented steps (dev aid)
             agg = {}
             for name, ms, a in rec:
                 key = name
-                if name.startswith("mmsb_linear_fwd") or name.startswith("mmsb_linear_bwd_weight"):
-                    key = f"{name} n={a[6].value} k={a[7].value} o={a[8].value}"
-                elif name.startswith("mmsb_linear_bwd_data"):
-                    key = f"{name} n={a[9].value} k={a[10].value} o={a[11].value}"
+                if name in LAYER:
+                    j = LAYER[name][1]
+                    key = f"{name} n={a[j].value} k={a[j + 1].value} o={a[j + 2].value}"
                 c = agg.setdefault(key, [0, 0.0])
                 c[0] += 1
                 c[1] += ms
@@ -272,35 +275,44 @@ def main():
                 fh.write(f"instrumented entry points: {tot / 2:.2f} ms per step\n")
                 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                     fh.write(f"{v[1] / 2:9.3f} ms/step {v[0] // 2:5d} calls  {k}\n")
-        keep = {"mmsb_linear_fwd", "mmsb_linear_bwd_data", "mmsb_linear_bwd_weight", "mmsb_hashgrid_fwd", "mmsb_hashgrid_bwd"}
-        rec = [r for r in rec if (r[0][:-3] if r[0].endswith("_tc") else r[0]) in keep]
+        flops = {"fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}
+        msk = {k: 0.0 for k in flops}
+        cnt = {k: 0 for k in flops}
+        hb = {"mmsb_hashgrid_fwd": [0.0, 0.0, 0], "mmsb_hashgrid_bwd": [0.0, 0.0, 0]}
         for name, ms, a in rec:
-            if name.endswith("_tc"):
-                name = name[:-3]
-                tc_ms += ms
-            if name == "mmsb_linear_fwd":
-                n, k, o = a[6].value, a[7].value, a[8].value
-            elif name == "mmsb_linear_bwd_data":
-                n, k, o = a[9].value, a[10].value, a[11].value
-            elif name == "mmsb_linear_bwd_weight":
-                n, k, o = a[6].value, a[7].value, a[8].value
-            else:
+            if name in LAYER:
+                cls, j = LAYER[name]
+                n, k, o = a[j].value, a[j + 1].value, a[j + 2].value
+                flops[cls] += 2.0 * n * k * o
+                msk[cls] += ms
+                cnt[cls] += 1
+                if name.endswith("_tc"):
+                    tc_ms += ms
+            elif name in hb:
                 n = a[-2].value
                 hb[name][0] += n * (1024.0 if name.endswith("fwd") else 2048.0)      # L*8*F*4 B per look-up (x2 read-modify-write)
                 hb[name][1] += ms
                 hb[name][2] += 1
-                continue
-            flops[name] += 2.0 * n * k * o
-            msk[name] += ms
-            cnt[name] += 1
         top = max(msk, key=lambda k: msk[k])
         if msk[top] > 0:
             ach = flops[top] / (msk[top] / 1e3) / 1e12
             from multimodalstudio_b200 import ops as _ops
             path = {0: "fp32 SIMT GEMM", 1: "tcgen05 TF32", 3: "tcgen05 3xTF32 (3 MMAs per product, fp32-accurate)"}[_ops.MLP_PRECISION]
-            roof = {"kernel": f"{top} ({path}; {100.0 * tc_ms / max(sum(msk.values()), 1e-9):.0f}% of layer time on tcgen05)", "bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s",
-                    "frac": ach / tf_sust, "traffic": None, "launches": cnt[top] // 2, "ms_per_step": msk[top] / 2,
-                    "peak_source": f"{peak_src} bf16 sustained (kernel timed inside a long step)"}
+            traffic, traffic_note = None, None
+            tp = os.path.join(ROOT, "profiles", "r1b_traffic.json")
+            if os.path.exists(tp):
+                tj = json.load(open(tp))
+                if top in tj:
+                    traffic, traffic_note = tj[top]["dram_bytes_per_launch"], tj[top]["note"]
+            roof = {"kernel": f"{KERNEL[top]} ({path}; {100.0 * tc_ms / max(sum(msk.values()), 1e-9):.0f}% of layer time on tcgen05)",
+                    "bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s",
+                    "frac": ach / tf_sust, "traffic": traffic, "traffic_note": traffic_note, "launches": cnt[top] // 2,
+                    "ms_per_step": msk[top] / 2,
+                    "peak_source": f"{peak_src} bf16 sustained (kernel timed inside a long step)",
+                    "achieved_is": "2*n*in*out algorithmic FLOP of every launch of this product class in one step / their summed CUDA-event time (all layer shapes, incl. the narrow HBM-bound ones)",
+                    # fp32-accurate products cost three TF32 MMAs each and TF32 runs at half the bf16 rate:
+                    "ceiling_3xtf32": tf_sust / 6.0, "frac_of_3xtf32_ceiling": ach / (tf_sust / 6.0),
+                    "per_class": {c: {"tflops": flops[c] / max(msk[c], 1e-9) / 1e9, "ms_per_step": msk[c] / 2, "launches": cnt[c] // 2} for c in flops}}
         hk = max(hb, key=lambda k: hb[k][1])
         if hb[hk][1] > 0:
             ach = hb[hk][0] / (hb[hk][1] / 1e3) / 1e9
