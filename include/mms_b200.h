@@ -177,6 +177,18 @@ int mmsb_linear_bwd_data_rank1_tc(const float* dz, int64_t lddz, const float* pa
                                   const float* head_w, mmsb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * A17  polarization head: Stokes vector of a sample -> intensities behind the 0 / 45 / 90 / 135 degree polarizers.
+ * ref: field_components/field_heads.py:90-106, model_components/polarizer.py:39-101.
+ * stokes [n,3] (row stride ld_stokes) = raw head output (leaky_relu on S0 applied here), directions / up_directions
+ * [n,3] contiguous, out [n,4].  bwd: d_directions / d_up_directions may be NULL (poses not optimised).
+ * ---------------------------------------------------------------------------------------------- */
+int mmsb_polarization_fwd(const float* stokes, int64_t ld_stokes, const float* directions, const float* up_directions,
+                          float* out, int64_t n, mmsb_stream_t stream);
+int mmsb_polarization_bwd(const float* stokes, int64_t ld_stokes, const float* directions, const float* up_directions,
+                          const float* d_out, float* d_stokes, float* d_directions, float* d_up_directions, int64_t n,
+                          mmsb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * A1/A2  ray generation.  ref: cameras/camera_optimizers.py:86-119, cameras/lie_groups.py:28-63,
  * model_components/ray_generators.py:54-81, cameras/cameras.py:460-703,
  * cameras/camera_utils.py:279-383, utils/poses.py:53-67

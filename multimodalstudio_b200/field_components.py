@@ -462,10 +462,8 @@ class PolarizationHead(ModalityHead):
 
     def forward(self, input_tensor, directions, up_directions):
         stokes = self.field(input_tensor)
-        s0 = torch.nn.functional.leaky_relu(stokes[..., 0:1])
-        stokes = torch.cat([s0, stokes[..., 1:]], dim=-1)
-        aligned = align_polarization_filters(stokes, directions, up_directions)
-        return stokes_to_intensity(aligned)
+        # leaky_relu(S0) + align_polarization_filters + stokes_to_intensity: one kernel (mmsb_polarization_fwd/bwd)
+        return ops.PolarizationFn.apply(stokes, directions, up_directions)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -699,6 +699,38 @@ def mlp_forward(x, weights: Sequence[torch.Tensor], biases: Sequence[Optional[to
 
 
 # ------------------------------------------------------------------------------------------------
+# polarization head post-processing (A17)
+# ------------------------------------------------------------------------------------------------
+class PolarizationFn(torch.autograd.Function):
+    """stokes [n,3] (raw head output), directions [n,3], up_directions [n,3] -> intensities [n,4]
+    (field_heads.py:101-105: leaky_relu(S0), align_polarization_filters, stokes_to_intensity)."""
+
+    @staticmethod
+    def forward(ctx, stokes, directions, up_directions):
+        s2 = _rows(stokes, 3)
+        d2, u2 = _f(directions).reshape(-1, 3), _f(up_directions).reshape(-1, 3)
+        n = s2.shape[0]
+        out = torch.empty((n, 4), device=s2.device, dtype=torch.float32)
+        call("mmsb_polarization_fwd", ptr(s2), _i64(s2.stride(0)), ptr(d2), ptr(u2), ptr(out), _i64(n), stream_ptr())
+        ctx.save_for_backward(s2, d2, u2)
+        ctx.shapes = (stokes.shape, directions.shape, up_directions.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        s2, d2, u2 = ctx.saved_tensors
+        n = s2.shape[0]
+        g = _f(d_out).reshape(n, 4)
+        ds = torch.empty((n, 3), device=s2.device, dtype=torch.float32)
+        dd = torch.empty((n, 3), device=s2.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        du = torch.empty((n, 3), device=s2.device, dtype=torch.float32) if ctx.needs_input_grad[2] else None
+        call("mmsb_polarization_bwd", ptr(s2), _i64(s2.stride(0)), ptr(d2), ptr(u2), ptr(g), ptr(ds), ptr(dd), ptr(du), _i64(n),
+             stream_ptr())
+        sh = ctx.shapes
+        return ds.reshape(sh[0]), (dd.reshape(sh[1]) if dd is not None else None), (du.reshape(sh[2]) if du is not None else None)
+
+
+# ------------------------------------------------------------------------------------------------
 # ray generation / collider (A1-A3)
 # ------------------------------------------------------------------------------------------------
 class RayGenFn(torch.autograd.Function):

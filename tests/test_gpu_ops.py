@@ -309,10 +309,34 @@ def test_render_golden():
     assert_close(bw[..., None], g.t("bg_weights"))
     (bw * g.t("bg_cot", DEV)[..., 0]).sum().backward()
     assert_close(dens.grad[..., None], g.t("bg_ddensity"), rtol=2e-5)
-    from multimodalstudio_b200.field_components import align_polarization_filters, stokes_to_intensity
-    st = g.t("pol_stokes", DEV)
-    st = torch.cat([torch.nn.functional.leaky_relu(st[:, :1]), st[:, 1:]], -1)
-    assert_close(stokes_to_intensity(align_polarization_filters(st, dirs, g.t("up", DEV))), g.t("pol_out"), rtol=2e-5)
+    # A17: the reference's polarization post-processing (fixture from the unmodified reference) through the fused kernel
+    assert_close(ops.PolarizationFn.apply(g.t("pol_stokes", DEV), dirs, g.t("up", DEV)), g.t("pol_out"), rtol=2e-5)
+
+
+@pytest.mark.parametrize("n", [1, 1000, 70001])
+def test_polarization_head_vs_oracle(n):
+    """mmsb_polarization_fwd / bwd against the oracle's torch restatement (field_heads.py:101-105, polarizer.py:39-101):
+    intensities and the gradients w.r.t. the Stokes vector, the ray direction and the camera up direction."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(n)
+    stokes = torch.randn(n, 3, generator=gen)
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1)
+    up = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1)
+    if n > 4:
+        up[0] = torch.nn.functional.normalize(torch.linalg.cross(d[0], torch.tensor([0.0, 0.0, 1.0])), dim=-1)   # clamped cos
+    cot = torch.randn(n, 4, generator=gen)
+    ref_in = [t.clone().requires_grad_(True) for t in (stokes, d, up)]
+    ref = O.polarization_post(*ref_in)
+    ref_g = torch.autograd.grad((ref * cot).sum(), ref_in)
+    got_in = [t.to(DEV).requires_grad_(True) for t in (stokes, d, up)]
+    got = ops.PolarizationFn.apply(*got_in)
+    got_g = torch.autograd.grad((got * cot.to(DEV)).sum(), got_in)
+    assert_close(got, ref, rtol=1e-5, atol=1e-6, what="intensities")
+    assert_close(got_g[0], ref_g[0], rtol=2e-5, atol=1e-6, what="d stokes")
+    # d theta / d u = -1 / sqrt(1 - u^2) reaches 70 towards the clamp, where one ulp of u moves it by 1e-3 relative:
+    # the few rows with |u| > 0.99 may miss the band
+    for a, r, name in zip(got_g[1:], ref_g[1:], ["d directions", "d up"]):
+        assert_close_but_kinks(a, r, rtol=2e-5, max_frac=2e-2, what=name)
 
 
 @pytest.mark.parametrize("n,s", [(1, 1), (3, 31), (257, 64), (100, 200), (33, 256)])
