@@ -128,10 +128,11 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int n, bool mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (mn_major ? (3u << 15) : 0u) | (uint32_t(n >> 3) << 17) |
          (uint32_t(TM >> 4) << 24);
 }
+// fp32 -> TF32 (10 explicit mantissa bits), round to nearest, ties away from zero: what cvt.rna.tf32.f32 computes for
+// finite inputs, written as one integer add and one mask (full-rate pipes; the cvt instruction is a quarter-rate
+// conversion and the operand producers execute 2 of them per element on the MMA's critical hand-shake path).
 __device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 // byte offset of 16-byte chunk c (4 fp32 along M/N) of k-row k in an MN-major SWIZZLE_128B_BASE32B tile whose 32-wide
 // panels hold TK k-rows each
@@ -622,10 +623,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = r_base + 16 * i;
-        split_store4<NPARTS>(a_hi, a_hi + PART, uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4),
-                             g.hd ? generate(v[i], hd[i]) : v[i]);
+        const uint32_t off = uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4);
+        if (g.dbg & 32) {   // dev: no hi/lo conversion
+          sts128(smem_u32(a_hi) + off, v[i]);
+          if (NPARTS == 2) sts128(smem_u32(a_hi + PART) + off, v[i]);
+        } else {
+          split_store4<NPARTS>(a_hi, a_hi + PART, off, g.hd ? generate(v[i], hd[i]) : v[i]);
+        }
       }
-      fence_async_smem();
+      if (!(g.dbg & 16)) fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * s);     // one arrival per warp (128 single arrivals would serialise)
       it += GROUPS;

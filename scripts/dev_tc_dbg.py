@@ -6,10 +6,11 @@ from multimodalstudio_b200 import ops
 n, k, o = 2097152, 256, 256
 x = torch.randn(n, k, device="cuda"); w = torch.randn(o, k, device="cuda") * 0.1; b = torch.randn(o, device="cuda")
 y = torch.empty(n, o, device="cuda")
-for prec in (3, 1):
+for prec in (3,):
     pw = ops.pack_weight(w, False, prec)
     for dbg, what in [(0, "full"), (1, "no A loads"), (2, "no stores"), (4, "no B copies"), (8, "no MMAs"), (3, "no A loads, no stores"),
-                      (7, "MMAs only"), (11, "B copies only"), (14, "A loads only"), (13, "stores only"), (15, "nothing")]:
+                      (7, "MMAs only"), (11, "B copies only"), (14, "A loads only"), (13, "stores only"), (15, "nothing"), (15 + 16, "nothing, no fence"), (15 + 32, "nothing, no conversion"),
+                      (15 + 48, "nothing, no fence, no conversion"), (16, "full, no fence (wrong results)")]:
         os.environ["MMSB_TC_DEBUG"] = str(dbg)
         for _ in range(2):
             ops.linear_fwd_tc(x, pw, b, o, 1, 1.0, prec, out=y)
