@@ -20,7 +20,9 @@
 //       SWIZZLE_128B_BASE32B tiles; the bias gradient (column sums of dz) is accumulated by the producers on the way;
 //       partial tiles are combined with coalesced fp32 reductions (red.global.add).
 #include "common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace mmsb {
 namespace tc {
@@ -92,6 +94,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// 2-D tensor-map copy (TMA): box {TK floats, TM rows} at (k0, m0) -> shared memory in the map's swizzle, bytes onto bar
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int k0, int m0, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(k0), "r"(m0), "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -510,23 +518,32 @@ struct RowsArgs {
   const float* hd; const float* hw; int hact; float hact_param;
 };
 
-template <int NPARTS, int EPI>
-__global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g) {
+// TMA_A: the A k-blocks are landed by tensor-map copies straight into the stage's "hi" tile (K-major SWIZZLE_128B); the
+// tensor core reads fp32 operands as TF32 by TRUNCATION (measured, scripts/dev_tf32_rounding.py), so the raw tile IS the
+// hi operand, hi = trunc(x), and the 8 converter warps only derive lo = rna(x - trunc(x)) from shared memory.  No global
+// load sits in a register (or on the hand-shake path) any more.  Needs 16-byte aligned rows of A and a stored operand;
+// otherwise (generated operand, odd leading dimension) the register-staged producers below are used.
+template <int NPARTS, int EPI, bool TMA_A>
+__global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g, const __grid_constant__ CUtensorMap tmap_a) {
   constexpr int S = num_stages(NPARTS);
   constexpr int STAGE = stage_bytes(NPARTS);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* stg_all = reinterpret_cast<float*>(smem + S * STAGE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * STAGE + STG_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
   const uint32_t bar_tfull = smem_u32(bars + 2 * MAX_STAGES), bar_tempty = smem_u32(bars + 2 * MAX_STAGES + 2);
+  const uint32_t bar_raw = smem_u32(bars + 2 * MAX_STAGES + 4);      // TMA_A: raw A tile landed
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   if (t == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(bar_full + 8 * s, 4 + 1);                // the four warps of one producer group + the B loader's expect_tx
+      // register path: the four warps of one producer group + the loader's expect_tx;
+      // TMA path: the 8 converter warps + the loader (3xTF32) or the loader alone (TF32: nothing to convert)
+      mbar_init(bar_full + 8 * s, TMA_A ? (NPARTS == 2 ? PROD_WARPS + 1 : 1) : 4 + 1);
       mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_raw + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
@@ -572,6 +589,33 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g) {
       });
     }
   } else if (warp < EPI_WARPS + PROD_WARPS) {
+    if constexpr (TMA_A) {
+      // ================= converters: lo = rna(x - trunc(x)) of the landed raw tile =================
+      if (NPARTS == 2) {
+        const int p = t - EPI_WARPS * 32;
+        const int64_t my_tiles = blockIdx.x < g.total_tiles ? (g.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t iters = my_tiles * g.nkb;
+        for (int64_t it = 0; it < iters; ++it) {
+          const uint32_t s = uint32_t(it % S);
+          mbar_wait(bar_raw + 8 * s, uint32_t(it / S) & 1);
+          const uint32_t hi = smem_u32(smem + s * STAGE), lo = hi + PART;
+#pragma unroll
+          for (int i = 0; i < PART / (PROD_THREADS * 16); ++i) {
+            const uint32_t off = uint32_t(p + i * PROD_THREADS) * 16u;     // element-wise: any mapping of the 16 KB works
+            const float4 x = lds128(hi + off);
+            float4 l;
+            l.x = tf32_rna(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+            l.y = tf32_rna(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+            l.z = tf32_rna(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+            l.w = tf32_rna(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+            sts128(lo + off, l);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_full + 8 * s);
+        }
+      }
+    } else {
     // ================= producers: A (global fp32) -> hi/lo -> swizzled shared memory =================
     // Two groups of four warps alternate over the k-blocks, each group owning one of the S = 2 stages (its own
     // mbarrier phases in order): a group's loads for its next k-block are in flight while the other group stores
@@ -637,6 +681,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g) {
       it += GROUPS;
       if (it < iters) load_block(it);
     }
+    }
   } else if (warp == EPI_WARPS + PROD_WARPS) {
     // ================= B loader: one bulk async copy per k-block =================
     if (lane == 0) {
@@ -646,9 +691,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g) {
         const int w = tile_width(n_pad, nt);
         const uint32_t bytes = uint32_t(NPARTS * w * 128);
         const float* src = g.Bp + int64_t(nt) * NT * TK * g.nkb * NPARTS;
+        const int m0 = int((tile / g.n_tiles) * TM);
         for (int kb = 0; kb < g.nkb; ++kb, ++it) {
           const uint32_t s = it % S;
           mbar_wait(bar_empty + 8 * s, ((it / S) & 1) ^ 1);
+          if constexpr (TMA_A) {
+            // raw A tile: 128 rows x 128 B (rows / columns past the tensor are zero-filled and still counted)
+            const uint32_t a_bar = NPARTS == 2 ? bar_raw + 8 * s : bar_full + 8 * s;
+            if (NPARTS == 2) mbar_arrive_expect_tx(a_bar, uint32_t(PART));
+            else mbar_arrive_expect_tx(a_bar, uint32_t(PART) + ((g.dbg & 4) ? 0u : bytes));
+            tma_load_2d(smem_u32(smem + s * STAGE), &tmap_a, kb * TK, m0, a_bar);
+            if (NPARTS == 1) {
+              if (!(g.dbg & 4))
+                bulk_g2s(smem_u32(smem + s * STAGE + NPARTS * PART), src + int64_t(kb) * NPARTS * w * TK, bytes, a_bar);
+              continue;
+            }
+          }
           if (g.dbg & 4) {
             mbar_arrive(bar_full + 8 * s);
           } else {
@@ -904,18 +962,58 @@ static int set_smem(K kern, int bytes, const char* what) {
   return MMSB_OK;
 }
 
-template <int NPARTS, int EPI>
-static int launch_rows(const RowsArgs& g, cudaStream_t s, const char* what) {
+template <int NPARTS, int EPI, bool TMA_A>
+static int launch_rows_impl(const RowsArgs& g, const CUtensorMap& map, cudaStream_t s, const char* what) {
   static bool configured = false;
-  auto kern = tc_rows_kernel<NPARTS, EPI>;
+  auto kern = tc_rows_kernel<NPARTS, EPI, TMA_A>;
   if (!configured) {
     int rc = set_smem(kern, smem_bytes(NPARTS), what);
     if (rc) return rc;
     configured = true;
   }
   const int64_t grid = g.total_tiles < kNumSMs ? g.total_tiles : kNumSMs;
-  kern<<<(unsigned)grid, THREADS, smem_bytes(NPARTS), s>>>(g);
+  kern<<<(unsigned)grid, THREADS, smem_bytes(NPARTS), s>>>(g, map);
   return check_launch(what);
+}
+
+// Tensor map of the A operand: [M rows, K floats] fp32, row stride lda floats, box 32 floats x 128 rows, SWIZZLE_128B.
+static bool make_a_map(const RowsArgs& g, CUtensorMap* map) {
+  static int use_tma = -1;
+  if (use_tma < 0) { const char* e = getenv("MMSB_TC_TMA"); use_tma = e ? atoi(e) : 1; }
+  if (!use_tma || g.hd != nullptr || (g.dbg & 1)) return false;
+  if ((reinterpret_cast<uintptr_t>(g.A) & 15) != 0 || (g.lda & 3) != 0 || g.M >= (int64_t(1) << 31)) return false;
+  const cuuint64_t dims[2] = {cuuint64_t(g.K), cuuint64_t(g.M)};
+  const cuuint64_t strides[1] = {cuuint64_t(g.lda) * sizeof(float)};
+  const cuuint32_t box[2] = {cuuint32_t(TK), cuuint32_t(TM)};
+  const cuuint32_t estr[2] = {1, 1};
+  // the driver entry point is resolved through the runtime (no link-time dependency on libcuda: the library must load,
+  // and export its symbols, on a machine without a driver)
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  static bool resolved = false;
+  if (!resolved) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<EncodeFn>(fn);
+    resolved = true;
+  }
+  if (encode == nullptr) return false;
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(g.A), dims, strides, box,
+                                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int NPARTS, int EPI>
+static int launch_rows(const RowsArgs& g, cudaStream_t s, const char* what) {
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (make_a_map(g, &map)) return launch_rows_impl<NPARTS, EPI, true>(g, map, s, what);
+  return launch_rows_impl<NPARTS, EPI, false>(g, map, s, what);
 }
 
 template <int NPARTS>
