@@ -319,6 +319,23 @@ def main():
             roof_hash = {"kernel": hk, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                          "traffic": None, "launches": hb[hk][2] // 2, "ms_per_step": hb[hk][1] / 2}
 
+    # full-frame inference: eval-mode rendering of 4 x the training batch in chunks, reported beside
+    # the headline metric (not part of it)
+    inference = None
+    if world == 1 and not args.no_e2e:
+        big = {m: torch.cat([resident[i][0][m] for i in range(n_batches)], 0) for m in mods}
+        n_inf = sum(c.shape[0] for c in big.values())
+        pipe.render(big)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            pipe.render(big)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_inf = e0.elapsed_time(e1) / 3
+        inference = {"value": n_inf / (ms_inf / 1e3), "unit": "rays/s", "rays": n_inf, "ms": ms_inf,
+                     "what": "RawPipeline.render: eval mode, no_grad, all modalities per chunk as one batch (eager launches)"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, ms, n_rays = cpu_reference_arm(wl, 2, 1)
@@ -329,7 +346,7 @@ def main():
         line = {"metric": "train rays/sec (fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": cfg_out, "clocks": clk, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roof, "roofline_hashgrid": roof_hash, "cpu_baseline": cpu, "impl": "b200"}
+                "roofline": roof, "roofline_hashgrid": roof_hash, "cpu_baseline": cpu, "inference": inference, "impl": "b200"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

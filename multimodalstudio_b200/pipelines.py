@@ -257,6 +257,37 @@ class RawPipeline:
         self.optimizer_step(step)
         return losses, total
 
+    # ---- full-frame inference (utils/eval_utils.py:31-75, engine/evaluator.py:619-746) ----------
+    @torch.no_grad()
+    def render(self, coords, chunk_rays: int = 32768):
+        """Renders pixel coordinates {mod: int32 [R,3]} in eval mode (deterministic sampling, no Hessian) in chunks of
+        `chunk_rays` rays per modality, all modalities of a chunk as one batch; returns {mod: [R, C]} (the modality's
+        own head; mosaicked pipelines select the pattern's channel per pixel like evaluator.py:721-746)."""
+        was_training = self.model.training
+        self.model.eval()
+        ops.clear_pack_cache()
+        out = {m: [] for m in coords}
+        n_max = max(c.shape[0] for c in coords.values())
+        try:
+            with torch.nn.utils.parametrize.cached():
+                for a in range(0, n_max, chunk_rays):
+                    part = {m: c[a:a + chunk_rays] for m, c in coords.items() if c.shape[0] > a}
+                    bundles = self.ray_generator(part)
+                    outputs = self.model(bundles)
+                    for m in part:
+                        out[m].append(outputs[m][m])
+        finally:
+            self.model.train(was_training)
+        rendered = {m: torch.cat(v, 0) for m, v in out.items() if v}
+        if self.raw:
+            selected = {}
+            for m, r in rendered.items():
+                pat = self.patterns[m]
+                _, sel = ops.mosaick_bands(coords[m], pat.reshape(-1), pat.shape[0], pat.shape[1], r)
+                selected[m] = sel[:, None]
+            return selected
+        return rendered
+
     # ---- the same step replayed from CUDA graphs ------------------------------------------------------------
     def _schedule_key(self, step, coords, targets):
         """Everything a captured step bakes into its launch arguments: the schedule state the callbacks set
