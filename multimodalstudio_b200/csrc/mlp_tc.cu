@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g, c
     for (int s = 0; s < S; ++s) {
       // register path: the four warps of one producer group + the loader's expect_tx;
       // TMA path: the 8 converter warps + the loader (3xTF32) or the loader alone (TF32: nothing to convert)
-      mbar_init(bar_full + 8 * s, TMA_A ? (NPARTS == 2 ? PROD_WARPS + 1 : 1) : 4 + 1);
+      mbar_init(bar_full + 8 * s, TMA_A ? ((NPARTS == 2 || g.hd != nullptr) ? PROD_WARPS + 1 : 1) : 4 + 1);
       mbar_init(bar_empty + 8 * s, 1);
       mbar_init(bar_raw + 8 * s, 1);
     }
@@ -591,24 +591,53 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g, c
   } else if (warp < EPI_WARPS + PROD_WARPS) {
     if constexpr (TMA_A) {
       // ================= converters: lo = rna(x - trunc(x)) of the landed raw tile =================
-      if (NPARTS == 2) {
+      // (generated operand, g.hd: the landed tile holds the stored activations y; it is overwritten in place with
+      //  a = hd[row] * hw[k] * act'(y), which the tensor core again reads truncated, and lo is derived from a)
+      if (NPARTS == 2 || g.hd != nullptr) {
         const int p = t - EPI_WARPS * 32;
         const int64_t my_tiles = blockIdx.x < g.total_tiles ? (g.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const int64_t iters = my_tiles * g.nkb;
+        const int c = p & 7, r_base = p >> 3;          // generated operand: 16-byte chunk c of rows r_base + 32 i
         for (int64_t it = 0; it < iters; ++it) {
           const uint32_t s = uint32_t(it % S);
+          float hd[4];
+          float4 hw4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g.hd) {
+            const int64_t tl = it / g.nkb;
+            const int kb = int(it - tl * g.nkb);
+            const int64_t m0 = ((blockIdx.x + tl * gridDim.x) / g.n_tiles) * TM;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int64_t row = m0 + r_base + 32 * i;
+              hd[i] = row < g.M ? __ldg(g.hd + row) : 0.f;
+            }
+            if (kb * TK + c * 4 < g.K) hw4 = load_cols4(g.hw, kb * TK + c * 4, g.K);
+          }
           mbar_wait(bar_raw + 8 * s, uint32_t(it / S) & 1);
           const uint32_t hi = smem_u32(smem + s * STAGE), lo = hi + PART;
 #pragma unroll
           for (int i = 0; i < PART / (PROD_THREADS * 16); ++i) {
-            const uint32_t off = uint32_t(p + i * PROD_THREADS) * 16u;     // element-wise: any mapping of the 16 KB works
-            const float4 x = lds128(hi + off);
-            float4 l;
-            l.x = tf32_rna(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
-            l.y = tf32_rna(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
-            l.z = tf32_rna(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
-            l.w = tf32_rna(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
-            sts128(lo + off, l);
+            uint32_t off = uint32_t(p + i * PROD_THREADS) * 16u;     // plain conversion is element-wise: any mapping works
+            if (g.hd) {
+              const int r = r_base + 32 * i;
+              off = uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4);
+            }
+            float4 x = lds128(hi + off);
+            if (g.hd) {
+              x.x = hd[i] * hw4.x * act_bwd_from_y(x.x, g.hact, g.hact_param);
+              x.y = hd[i] * hw4.y * act_bwd_from_y(x.y, g.hact, g.hact_param);
+              x.z = hd[i] * hw4.z * act_bwd_from_y(x.z, g.hact, g.hact_param);
+              x.w = hd[i] * hw4.w * act_bwd_from_y(x.w, g.hact, g.hact_param);
+              sts128(hi + off, x);
+            }
+            if (NPARTS == 2) {
+              float4 l;
+              l.x = tf32_rna(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+              l.y = tf32_rna(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+              l.z = tf32_rna(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+              l.w = tf32_rna(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+              sts128(lo + off, l);
+            }
           }
           fence_async_smem();
           __syncwarp();
@@ -697,11 +726,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g, c
           mbar_wait(bar_empty + 8 * s, ((it / S) & 1) ^ 1);
           if constexpr (TMA_A) {
             // raw A tile: 128 rows x 128 B (rows / columns past the tensor are zero-filled and still counted)
-            const uint32_t a_bar = NPARTS == 2 ? bar_raw + 8 * s : bar_full + 8 * s;
-            if (NPARTS == 2) mbar_arrive_expect_tx(a_bar, uint32_t(PART));
+            const bool conv = NPARTS == 2 || g.hd != nullptr;
+            const uint32_t a_bar = conv ? bar_raw + 8 * s : bar_full + 8 * s;
+            if (conv) mbar_arrive_expect_tx(a_bar, uint32_t(PART));
             else mbar_arrive_expect_tx(a_bar, uint32_t(PART) + ((g.dbg & 4) ? 0u : bytes));
             tma_load_2d(smem_u32(smem + s * STAGE), &tmap_a, kb * TK, m0, a_bar);
-            if (NPARTS == 1) {
+            if (!conv) {
               if (!(g.dbg & 4))
                 bulk_g2s(smem_u32(smem + s * STAGE + NPARTS * PART), src + int64_t(kb) * NPARTS * w * TK, bytes, a_bar);
               continue;
@@ -980,7 +1010,7 @@ static int launch_rows_impl(const RowsArgs& g, const CUtensorMap& map, cudaStrea
 static bool make_a_map(const RowsArgs& g, CUtensorMap* map) {
   static int use_tma = -1;
   if (use_tma < 0) { const char* e = getenv("MMSB_TC_TMA"); use_tma = e ? atoi(e) : 1; }
-  if (!use_tma || g.hd != nullptr || (g.dbg & 1)) return false;
+  if (!use_tma || (g.dbg & 1)) return false;
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) != 0 || (g.lda & 3) != 0 || g.M >= (int64_t(1) << 31)) return false;
   const cuuint64_t dims[2] = {cuuint64_t(g.K), cuuint64_t(g.M)};
   const cuuint64_t strides[1] = {cuuint64_t(g.lda) * sizeof(float)};
