@@ -516,6 +516,7 @@ struct RowsArgs {
   // generated operand (dgrad below a fused head): A[r, k] = hd[r] * hw[k] * act'(A_mem[r, k]), A_mem = the stored
   // activations of the layer
   const float* hd; const float* hw; int hact; float hact_param;
+  int stages, stage_bytes;   // ring geometry of this launch (set by launch_rows)
 };
 
 // TMA_A: the A k-blocks are landed by tensor-map copies straight into the stage's "hi" tile (K-major SWIZZLE_128B); the
@@ -525,12 +526,15 @@ struct RowsArgs {
 // otherwise (generated operand, odd leading dimension) the register-staged producers below are used.
 template <int NPARTS, int EPI, bool TMA_A>
 __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g, const __grid_constant__ CUtensorMap tmap_a) {
-  constexpr int S = num_stages(NPARTS);
-  constexpr int STAGE = stage_bytes(NPARTS);
+  // stages: as many as fit into the ring (2 x 96 KB) for this launch's widest B tile — 2 for a 256-wide accumulator,
+  // 3..4 for narrow layers (their MMAs are short, so the stage refill latency is what a deeper ring hides)
+  constexpr int RING = num_stages(NPARTS) * stage_bytes(NPARTS);
+  const int STAGE = g.stage_bytes;
+  const int S = g.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* stg_all = reinterpret_cast<float*>(smem + S * STAGE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * STAGE + STG_BYTES);
+  float* stg_all = reinterpret_cast<float*>(smem + RING);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING + STG_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
   const uint32_t bar_tfull = smem_u32(bars + 2 * MAX_STAGES), bar_tempty = smem_u32(bars + 2 * MAX_STAGES + 2);
@@ -652,7 +656,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g, c
     // ring slots share scoreboard entries, so the wait for the oldest slot also waits for the newest.  More groups
     // than stages would alias the mbarrier phase parities.)
     constexpr int GROUPS = PROD_WARPS / 4;
-    static_assert(GROUPS == 2 && S % GROUPS == 0, "a producer group must always meet the same stages");
+    static_assert(GROUPS == 2, "two producer groups");      // the host picks an even stage count for this path
     const int p = t - EPI_WARPS * 32;
     const int grp = p >> 7, q = p & 127;
     const int c = q & 7, r_base = q >> 3;          // 16-byte chunk c of rows r_base + 16 i
@@ -1039,10 +1043,20 @@ static bool make_a_map(const RowsArgs& g, CUtensorMap* map) {
 }
 
 template <int NPARTS, int EPI>
-static int launch_rows(const RowsArgs& g, cudaStream_t s, const char* what) {
+static int launch_rows(const RowsArgs& g_in, cudaStream_t s, const char* what) {
+  RowsArgs g = g_in;
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
-  if (make_a_map(g, &map)) return launch_rows_impl<NPARTS, EPI, true>(g, map, s, what);
+  const bool tma = make_a_map(g, &map);
+  // ring geometry: stage = A hi [+ lo] + the widest B tile of this launch (1024-byte multiple)
+  const int n_pad = pad16(g.N);
+  const int w_max = n_pad < NT ? n_pad : NT;
+  g.stage_bytes = (NPARTS * (PART + w_max * 128) + 1023) / 1024 * 1024;
+  int stages = num_stages(NPARTS) * stage_bytes(NPARTS) / g.stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (!tma && (stages & 1)) --stages;       // register-staged producers: each of the two groups owns its stages
+  g.stages = stages;
+  if (tma) return launch_rows_impl<NPARTS, EPI, true>(g, map, s, what);
   return launch_rows_impl<NPARTS, EPI, false>(g, map, s, what);
 }
 
