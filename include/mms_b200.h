@@ -370,6 +370,14 @@ int mmsb_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* 
 /* sumsq[0] += sum grad^2 (for clip_grad_norm_, pipelines/base_pipeline.py:232-248). */
 int mmsb_sumsq(const float* x, float* sumsq, int64_t n, mmsb_stream_t stream);
 
+/* SURVEY 8(f) row 2  on-device pixel sampling + target gather.
+ * ref: cameras/pixel_samplers.py:71-89 (uniform (camera, y, x) per ray), data/dataloaders.py:164-167 (target gather).
+ * coords int32 [n,3]; frames [n_cam, height, width, channels] fp32 device-resident (or NULL: indices only) ->
+ * targets [n, channels].  Counter-based (Philox-4x32-10): the draw of ray i depends only on (seed, step, stream_id, i). */
+int mmsb_sample_pixels(uint64_t seed, int32_t step, int32_t stream_id, int32_t n_cam, int32_t height, int32_t width,
+                       const float* frames, int32_t channels, int32_t* coords, float* targets, int64_t n,
+                       mmsb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

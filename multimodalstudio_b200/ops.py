@@ -1097,3 +1097,19 @@ def adamw_step_dev(param, grad, exp_avg, exp_avg_sq, grad_sumsq, max_norm, hyper
     """hyper: device tensor [3] = {lr, 1 - beta1^t, sqrt(1 - beta2^t)} (graph-replayable AdamW)."""
     call("mmsb_adamw_step_dev", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(grad_sumsq), _f32(max_norm or 0.0),
          ptr(hyper), _f32(beta1), _f32(beta2), _f32(eps), _f32(weight_decay), _i64(param.numel()), stream_ptr())
+
+
+def sample_pixels(seed: int, step: int, stream_id: int, n_cam: int, height: int, width: int, n: int, device, frames=None):
+    """(camera, y, x) int32 [n,3] drawn on the device (+ targets [n,C] gathered from frames [n_cam,H,W,C] when given)."""
+    coords = torch.empty((n, 3), device=device, dtype=torch.int32)
+    targets, channels = None, 0
+    if frames is not None:
+        if not frames.is_cuda or frames.dtype != torch.float32 or not frames.is_contiguous() or frames.dim() != 4:
+            raise ValueError("frames must be a contiguous fp32 CUDA tensor [n_cam, H, W, C]")
+        if tuple(frames.shape[:3]) != (n_cam, height, width):
+            raise ValueError(f"frames {tuple(frames.shape)} do not match n_cam={n_cam} H={height} W={width}")
+        channels = frames.shape[3]
+        targets = torch.empty((n, channels), device=device, dtype=torch.float32)
+    call("mmsb_sample_pixels", ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), _i32(step), _i32(stream_id), _i32(n_cam), _i32(height),
+         _i32(width), ptr(frames), _i32(channels), ptr(coords), ptr(targets), _i64(n), stream_ptr())
+    return coords, targets

@@ -86,6 +86,24 @@ class SyntheticScene:
         return coords, targets
 
 
+class DevicePixelSampler:
+    """UniformPixelSampler + the loader's target gather on the device (pixel_samplers.py:71-89,
+    dataloaders.py:164-167): `frames` {mod: fp32 [n_cam, H, W, C]} stay resident in HBM (raw mosaicked stacks have
+    C = 1), `sample(step)` returns coords {mod: int32 [R,3]} and targets {mod: [R,C]} without touching the host.  Uniform
+    like the reference, not the same sequence (counter-based Philox instead of torch's CPU generator); the rank offsets
+    the seed like pixel_samplers.py:49-52."""
+
+    def __init__(self, frames: Dict[str, torch.Tensor], rays_per_modality: Dict[str, int], seed: int = 654824, rank: int = 0):
+        self.frames, self.rays, self.seed = frames, rays_per_modality, seed + rank
+
+    def sample(self, step: int):
+        coords, targets = {}, {}
+        for i, (mod, fr) in enumerate(self.frames.items()):
+            n_cam, h, w, _ = fr.shape
+            coords[mod], targets[mod] = ops.sample_pixels(self.seed, step, i, n_cam, h, w, self.rays[mod], fr.device, fr)
+        return coords, targets
+
+
 class FlatAdamW:
     """One AdamW "optimizer" of the reference (engine/optimizers.py, method_configs.py:260-269) over a flat
     fp32 buffer: parameters and gradients are views into two contiguous tensors, so zero-grad is one memset,
@@ -287,6 +305,28 @@ class RawPipeline:
                 selected[m] = sel[:, None]
             return selected
         return rendered
+
+    # ---- SDF volume sweep for mesh extraction (utils/marching_cubes.py:34-188) ---------------------
+    @torch.no_grad()
+    def sdf_volume(self, resolution: int = 256, bounding_box_min=(-1.0, -1.0, -1.0), bounding_box_max=(1.0, 1.0, 1.0),
+                   chunk_points: int = 1 << 21):
+        """sdf on the regular grid linspace(min, max, resolution)^3 (indexing "ij" like get_surface_sliding) ->
+        [resolution]^3 fp32.  A pure consumer of the fused SDF forward (encodings + layer 0 + layer 1 with the sdf head in
+        its epilogue; no activation is stored); marching cubes itself stays with the caller."""
+        dev = self.device
+        axes = [torch.linspace(float(a), float(b), resolution, device=dev) for a, b in zip(bounding_box_min, bounding_box_max)]
+        ops.clear_pack_cache()
+        out = torch.empty((resolution ** 3,), device=dev, dtype=torch.float32)
+        yz = torch.cartesian_prod(axes[1], axes[2])                       # [res^2, 2], y-major
+        slabs = max(1, chunk_points // (resolution * resolution))
+        field = self.model.surface_model.surface_field
+        with torch.nn.utils.parametrize.cached():
+            for i0 in range(0, resolution, slabs):
+                xs = axes[0][i0:i0 + slabs]
+                pts = torch.cat([xs[:, None, None].expand(-1, yz.shape[0], 1), yz[None].expand(xs.shape[0], -1, -1)], -1)
+                sdf = field.single_output(pts.reshape(-1, 3))
+                out[i0 * resolution * resolution:(i0 + xs.shape[0]) * resolution * resolution] = sdf.reshape(-1)
+        return out.reshape(resolution, resolution, resolution)
 
     # ---- the same step replayed from CUDA graphs ------------------------------------------------------------
     def _schedule_key(self, step, coords, targets):

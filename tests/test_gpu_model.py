@@ -244,3 +244,21 @@ def test_render_driver_matches_single_batch_eval():
         assert got[m].shape == (rays[m], 1)
         # chunks see a different global depth clip only; colours are per-ray
         assert_close(got[m], ref, rtol=1e-6, atol=1e-7, what=m)
+
+
+def test_sdf_volume_matches_oracle():
+    """RawPipeline.sdf_volume (mesh-extraction sweep) against the oracle's SDF field on a 12^3 grid, chunked."""
+    from multimodalstudio_b200.pipelines import RawPipeline, SyntheticScene
+    mods = {"mono": 1}
+    scene = SyntheticScene(mods, {"mono": 8}, seed=2)
+    pipe = RawPipeline(mods, scene.cameras, device=DEV, raw=True, log2_hashmap_size=12, seed=9)
+    pipe.model.set_schedule_state(16, 2.0 / 1024, 1.0)
+    vol = pipe.sdf_volume(12, chunk_points=300)
+    assert vol.shape == (12, 12, 12)
+    sd = {k: v.detach().cpu() for k, v in pipe.model.state_dict().items()}
+    orc = O.GridModelOracle(sd, O.default_cfg(modalities=mods, log2_hashmap_size=12))
+    ax = torch.linspace(-1.0, 1.0, 12)
+    pts = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
+    with torch.no_grad():
+        ref = orc.sdf_field(pts)[0].reshape(12, 12, 12)
+    assert_close(vol, ref, rtol=3e-5, atol=1e-6, what="sdf volume")

@@ -506,3 +506,26 @@ def test_sdf_net_fused_head_vs_fp64(n, n_full):
         if r is None:
             r = torch.zeros_like(a)
         assert_close(a, r, rtol=3e-5, atol=1e-7, what=name)
+
+
+def test_device_pixel_sampler():
+    """mmsb_sample_pixels: range, determinism in (seed, step, stream), uniformity, exact target gather."""
+    ops = _ops()
+    n_cam, h, w, c, n = 7, 37, 53, 3, 200_000
+    frames = torch.rand(n_cam, h, w, c, device=DEV)
+    co, tg = ops.sample_pixels(1234, 5, 0, n_cam, h, w, n, DEV, frames)
+    co2, tg2 = ops.sample_pixels(1234, 5, 0, n_cam, h, w, n, DEV, frames)
+    assert torch.equal(co, co2) and torch.equal(tg, tg2)
+    for other in (ops.sample_pixels(1234, 6, 0, n_cam, h, w, n, DEV)[0], ops.sample_pixels(1234, 5, 1, n_cam, h, w, n, DEV)[0],
+                  ops.sample_pixels(1235, 5, 0, n_cam, h, w, n, DEV)[0]):
+        assert float((other == co).all(dim=1).float().mean()) < 0.01
+    cl = co.long()
+    assert int(cl[:, 0].min()) >= 0 and int(cl[:, 0].max()) == n_cam - 1
+    assert int(cl[:, 1].min()) >= 0 and int(cl[:, 1].max()) == h - 1
+    assert int(cl[:, 2].min()) >= 0 and int(cl[:, 2].max()) == w - 1
+    assert torch.equal(tg, frames[cl[:, 0], cl[:, 1], cl[:, 2]])
+    for j, rng in enumerate((n_cam, h, w)):      # every value about equally often (5 sigma of a binomial count)
+        counts = torch.bincount(cl[:, j], minlength=rng).double()
+        exp = n / rng
+        assert float((counts - exp).abs().max()) < 5.0 * (exp * (1 - 1 / rng)) ** 0.5 + 1
+    assert ops.sample_pixels(1, 0, 0, 3, 4, 5, 0, DEV)[0].shape == (0, 3)
