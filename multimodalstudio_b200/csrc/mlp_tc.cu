@@ -185,6 +185,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 256 bits (8 fp32 columns) per repetition, the mma C-fragment layout: thread t holds (row t / 4, columns
+// 2 (t % 4), +1) in v[0..1] and (row t / 4 + 8, same columns) in v[2..3]; the second repetition (v[4..7]) is the next 8
+// columns.  A quad of lanes therefore owns a whole 32-byte sector of a row: global stores need no transpose.
+__device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // The epilogues evaluate Softplus through the MUFU units (ex2 / lg2 approximations, ~2^-22 relative): their error is
@@ -256,8 +265,7 @@ enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_ATOMIC = 2 };
 struct EpiArgs {
   float* C; int64_t ldc; int64_t M; int N;   // logical extents of C
   int64_t cs;                                // column stride of C for the reducing epilogue (0 = 1; != 1: transposed store)
-  int direct;                                // forward: store from the TMEM register layout (lane = row) without the
-                                             // shared-memory transpose (needs 16-byte aligned rows of C)
+  int direct;                                // 2: fragment-layout epilogue (no shared-memory transpose), 0: transposed
   const float* bias; int act; float act_param;
   const float* yprev; int64_t ld_yprev; int act_prev; float act_prev_param;
   // forward with a fused one-output head: head_out[row] += sum_col act(z)[row, col] * head_w[col] (+ head_b once);
@@ -372,51 +380,10 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& e, const float* stg
   }
 }
 
-// Forward chunk without the transpose: the lane keeps its row's CH consecutive columns (64 contiguous bytes) and
-// stores them itself.  The two 16-byte halves of a 32-byte sector come from consecutive instructions of the same
-// lane, so they meet in the L2; no shared-memory traffic, no warp synchronisation.
-template <int ACT>
-__device__ __forceinline__ void epilogue_chunk_direct(const EpiArgs& e, uint32_t (&v)[CH], int lane, int64_t row0, int col0,
-                                                      float (&hacc)[4]) {
-  const int64_t row = row0 + lane;
-#pragma unroll
-  for (int j = 0; j < CH / 4; ++j) {
-    const int col = col0 + 4 * j;
-    if (col >= e.N) break;
-    const float4 b4 = load_cols4(e.bias, col, e.N);
-    float4 x = make_float4(__uint_as_float(v[4 * j]) + b4.x, __uint_as_float(v[4 * j + 1]) + b4.y,
-                           __uint_as_float(v[4 * j + 2]) + b4.z, __uint_as_float(v[4 * j + 3]) + b4.w);
-    x = act_fwd4<ACT>(x, e.act_param);
-    if (e.head_w) {
-      const float4 h4 = load_cols4(e.head_w, col, e.N);
-      hacc[0] = fmaf(x.x, h4.x, fmaf(x.y, h4.y, fmaf(x.z, h4.z, fmaf(x.w, h4.w, hacc[0]))));
-    }
-    if (e.C != nullptr && row < e.M) {
-      float* dst = e.C + row * e.ldc + col;
-      if (col + 3 < e.N) {
-        *reinterpret_cast<float4*>(dst) = x;
-      } else {
-        dst[0] = x.x;
-        if (col + 1 < e.N) dst[1] = x.y;
-        if (col + 2 < e.N) dst[2] = x.z;
-      }
-    }
-  }
-}
-
 // One chunk: lane owns row (row0 + lane) in registers -> transpose buffer -> epilogue_rows.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, uint32_t (&v)[CH], float* stg, const YPrev& yp, int lane,
                                                int64_t row0, int col0, bool vec_ok, float (&hacc)[4]) {
-  if (EPI == EPI_FWD && e.direct) {
-    switch (e.act) {
-      case MMSB_ACT_RELU: epilogue_chunk_direct<MMSB_ACT_RELU>(e, v, lane, row0, col0, hacc); break;
-      case MMSB_ACT_SOFTPLUS: epilogue_chunk_direct<MMSB_ACT_SOFTPLUS>(e, v, lane, row0, col0, hacc); break;
-      case MMSB_ACT_SIGMOID: epilogue_chunk_direct<MMSB_ACT_SIGMOID>(e, v, lane, row0, col0, hacc); break;
-      default: epilogue_chunk_direct<MMSB_ACT_NONE>(e, v, lane, row0, col0, hacc); break;
-    }
-    return;
-  }
 #pragma unroll
   for (int j = 0; j < CH / 4; ++j)
     sts128(smem_u32(stg + lane * STG_LD + 4 * j),
@@ -431,6 +398,100 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, uint32_t (&v)[C
     default: epilogue_rows<EPI, MMSB_ACT_NONE>(e, stg, yp, lane, row0, col0, vec_ok, hacc); break;
   }
   __syncwarp();
+}
+
+// Chunk epilogue straight from the fragment layout (EpiArgs::direct == 2): 32 rows x CH columns, no shared memory.
+// va / vb: the two tmem_ld_frag results (rows 0..15 / 16..31 of the warp's TMEM lanes); yv: derivative operand (dgrad).
+struct YFrag {
+  float2 v[2][4];   // [8-column block][row (lane >> 2) + 8 i]
+  float d[4];
+};
+
+template <int EPI>
+__device__ __forceinline__ void load_yfrag(const EpiArgs& e, YFrag& y, int lane, int64_t row0, int col0) {
+  if (EPI != EPI_DGRAD) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t row = row0 + (lane >> 2) + 8 * i;
+    if (e.r1_d) y.d[i] = row < e.M ? __ldg(e.r1_d + row) : 0.f;
+    if (e.yprev != nullptr && e.act_prev != MMSB_ACT_NONE) {
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        const int col = col0 + 8 * blk + 2 * (lane & 3);
+        float2 v = make_float2(0.f, 0.f);
+        if (row < e.M && col < e.N) {
+          const float* p = e.yprev + row * e.ld_yprev + col;
+          if (col + 1 < e.N && (reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+            v = __ldg(reinterpret_cast<const float2*>(p));
+          } else {
+            v.x = __ldg(p);
+            if (col + 1 < e.N) v.y = __ldg(p + 1);
+          }
+        }
+        y.v[blk][i] = v;
+      }
+    }
+  }
+}
+
+template <int EPI, int ACT>
+__device__ __forceinline__ void epilogue_chunk_frag(const EpiArgs& e, const uint32_t (&va)[8], const uint32_t (&vb)[8],
+                                                    const YFrag& y, int lane, int64_t row0, int col0, float (&hacc)[4]) {
+  const int q4 = lane & 3;
+#pragma unroll
+  for (int blk = 0; blk < 2; ++blk) {
+    const int col = col0 + 8 * blk + 2 * q4;
+    if (col >= e.N) continue;
+    const bool two = col + 1 < e.N;
+    float b0 = 0.f, b1 = 0.f, h0 = 0.f, h1 = 0.f, r0 = 0.f, r1 = 0.f;
+    if (EPI == EPI_FWD) {
+      if (e.bias) { b0 = __ldg(e.bias + col); if (two) b1 = __ldg(e.bias + col + 1); }
+      if (e.head_w) { h0 = __ldg(e.head_w + col); if (two) h1 = __ldg(e.head_w + col + 1); }
+    } else if (e.r1_w) {
+      r0 = __ldg(e.r1_w + col);
+      if (two) r1 = __ldg(e.r1_w + col + 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                      // rows (lane >> 2) + 8 i, like the transposed layout
+      const uint32_t* v = i < 2 ? va : vb;
+      const int o = 4 * blk + 2 * (i & 1);
+      const int64_t row = row0 + (lane >> 2) + 8 * i;
+      float x0 = __uint_as_float(v[o]), x1 = __uint_as_float(v[o + 1]);
+      if (EPI == EPI_FWD) {
+        x0 = act_fwd(x0 + b0, ACT, e.act_param);
+        x1 = act_fwd(x1 + b1, ACT, e.act_param);
+        if (e.head_w) hacc[i] = fmaf(x0, h0, fmaf(x1, h1, hacc[i]));
+      } else {
+        if (e.r1_d) { x0 = fmaf(y.d[i], r0, x0); x1 = fmaf(y.d[i], r1, x1); }
+        if (ACT != MMSB_ACT_NONE) {
+          x0 *= act_bwd_from_y(y.v[blk][i].x, ACT, e.act_prev_param);
+          x1 *= act_bwd_from_y(y.v[blk][i].y, ACT, e.act_prev_param);
+        }
+      }
+      if (e.C != nullptr && row < e.M) {
+        float* dst = e.C + row * e.ldc + col;
+        if (two && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+          *reinterpret_cast<float2*>(dst) = make_float2(x0, x1);
+        } else {
+          dst[0] = x0;
+          if (two) dst[1] = x1;
+        }
+      }
+    }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk_frag_dispatch(const EpiArgs& e, const uint32_t (&va)[8], const uint32_t (&vb)[8],
+                                                             const YFrag& y, int lane, int64_t row0, int col0,
+                                                             float (&hacc)[4]) {
+  const int act = EPI == EPI_FWD ? e.act : (e.yprev ? e.act_prev : MMSB_ACT_NONE);
+  switch (act) {
+    case MMSB_ACT_RELU: epilogue_chunk_frag<EPI, MMSB_ACT_RELU>(e, va, vb, y, lane, row0, col0, hacc); break;
+    case MMSB_ACT_SOFTPLUS: epilogue_chunk_frag<EPI, MMSB_ACT_SOFTPLUS>(e, va, vb, y, lane, row0, col0, hacc); break;
+    case MMSB_ACT_SIGMOID: epilogue_chunk_frag<EPI, MMSB_ACT_SIGMOID>(e, va, vb, y, lane, row0, col0, hacc); break;
+    default: epilogue_chunk_frag<EPI, MMSB_ACT_NONE>(e, va, vb, y, lane, row0, col0, hacc); break;
+  }
 }
 
 // All chunks of one accumulator that belong to this warp (quadrant q = warp % 4, chunks c = warp / 4, + EPI_WARPS / 4, ...).
@@ -448,11 +509,6 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
   // (two warps per row -> two commutative additions onto the caller's zeros: order-independent)
   auto head_flush = [&]() {
     if (EPI != EPI_FWD || e.head_w == nullptr) return;
-    if (e.direct) {   // the lane owns one row
-      const int64_t row = row0 + lane;
-      if (row < e.M) atomicAdd(e.head_out + row, hacc[0] + ((first == 0 && col_base == 0 && e.head_b) ? __ldg(e.head_b) : 0.f));
-      return;
-    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float v = hacc[i];
@@ -480,6 +536,51 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
       if (c + STEP < nch) load_yprev<EPI>(e, y_next, lane, row0, col_base + (c + STEP) * CH, vec_y);
       epilogue_chunk<EPI>(e, v, stg, y_cur, lane, row0, col_base + c * CH, vec_ok, hacc);
       if (c + STEP < nch) y_cur = y_next;
+    }
+    return;
+  }
+  if (EPI != EPI_ATOMIC && e.direct == 2) {
+    // fragment-layout epilogue, software-pipelined: the TMEM reads (and the derivative operand) of the warp's next
+    // chunk are in flight while the current one is processed
+    const uint32_t tbase = tmem_acc + (uint32_t(q * 32) << 16);
+    if constexpr (EPI == EPI_FWD) {
+      YFrag ynone;
+      for (int c = first; c < nch; c += STEP) {
+        uint32_t va[8], vb[8];
+        tmem_ld_frag(tbase + uint32_t(c * CH), va);
+        tmem_ld_frag(tbase + uint32_t(c * CH) + (16u << 16), vb);
+        tmem_ld_wait();
+        if (c + STEP >= nch) release();
+        epilogue_chunk_frag_dispatch<EPI>(e, va, vb, ynone, lane, row0, col_base + c * CH, hacc);
+      }
+    } else {
+      // dgrad: the derivative operand of the next chunk is what is kept in flight (registers do not allow both)
+      uint32_t va[8], vb[8];
+      YFrag ycur, ynext;
+      load_yfrag<EPI>(e, ycur, lane, row0, col_base + first * CH);
+      for (int c = first; c < nch; c += STEP) {
+        const int cn = c + STEP;
+        tmem_ld_frag(tbase + uint32_t(c * CH), va);
+        tmem_ld_frag(tbase + uint32_t(c * CH) + (16u << 16), vb);
+        if (cn < nch) load_yfrag<EPI>(e, ynext, lane, row0, col_base + cn * CH);
+        tmem_ld_wait();
+        if (cn >= nch) release();
+        epilogue_chunk_frag_dispatch<EPI>(e, va, vb, ycur, lane, row0, col_base + c * CH, hacc);
+        if (cn < nch) ycur = ynext;
+      }
+    }
+    if (EPI == EPI_FWD && e.head_w != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v = hacc[i];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        const int64_t row = row0 + (lane >> 2) + 8 * i;
+        if ((lane & 3) == 0 && row < e.M) {
+          if (first == 0 && col_base == 0 && e.head_b) v += __ldg(e.head_b);
+          atomicAdd(e.head_out + row, v);
+        }
+      }
     }
     return;
   }
@@ -1098,6 +1199,14 @@ extern "C" int mmsb_linear_pack_weight(const float* w, int64_t ldw, int32_t out_
   return check_launch("linear_pack_weight");
 }
 
+// Epilogue variant (MMSB_TC_DIRECT): 2 = fragment layout (tcgen05.ld.16x256b: a quad of lanes owns a 32-byte sector of a
+// row, no shared-memory transpose), 0 = 32x32b + transpose through shared memory (default; the two measure the same).
+static int epilogue_mode() {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("MMSB_TC_DIRECT"); mode = e ? atoi(e) : 0; }
+  return mode;
+}
+
 // ---- internal launch helpers shared by the plain and the fused-head entry points ----------------------------------
 static int rows_fwd(const float* x, int64_t ldx, const float* packed_w, const float* b, float* y, int64_t ldy, int64_t n,
                     int in_dim, int out_dim, int act, float act_param, int precision, const float* head_w,
@@ -1106,11 +1215,7 @@ static int rows_fwd(const float* x, int64_t ldx, const float* packed_w, const fl
   g.A = x; g.lda = ldx; g.M = n; g.K = in_dim; g.Bp = packed_w; g.N = out_dim;
   g.epi.C = y; g.epi.ldc = ldy; g.epi.M = n; g.epi.N = out_dim; g.epi.bias = b; g.epi.act = act; g.epi.act_param = act_param;
   g.epi.head_w = head_w; g.epi.head_b = head_b; g.epi.head_out = head_out;
-  {
-    static int direct = -1;
-    if (direct < 0) { const char* e = getenv("MMSB_TC_DIRECT"); direct = e ? atoi(e) : 0; }   // measured slower than the staged transpose (uncoalesced 16-byte stores): off by default
-    g.epi.direct = direct && (y == nullptr || ((ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0));
-  }
+  g.epi.direct = epilogue_mode();
   g.n_tiles = int(ceil_div(tc::pad16(out_dim), tc::NT)); g.nkb = int(ceil_div(in_dim, tc::TK));
   g.total_tiles = ceil_div(n, tc::TM) * g.n_tiles;
   { const char* e = getenv("MMSB_TC_DEBUG"); g.dbg = e ? atoi(e) : 0; }
@@ -1126,6 +1231,7 @@ static int rows_dgrad(const float* a, int64_t lda, const float* packed_wt, float
   g.epi.C = dx; g.epi.ldc = lddx; g.epi.M = n; g.epi.N = in_dim;
   g.epi.yprev = y_prev; g.epi.ld_yprev = ld_yprev; g.epi.act_prev = act_prev; g.epi.act_prev_param = act_prev_param;
   g.epi.r1_d = r1_d; g.epi.r1_w = r1_w;
+  g.epi.direct = epilogue_mode();
   g.hd = hd; g.hw = hw; g.hact = hact; g.hact_param = hact_param;
   g.n_tiles = int(ceil_div(tc::pad16(in_dim), tc::NT)); g.nkb = int(ceil_div(out_dim, tc::TK));
   g.total_tiles = ceil_div(n, tc::TM) * g.n_tiles;
