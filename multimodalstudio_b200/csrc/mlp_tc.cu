@@ -27,6 +27,13 @@
 namespace mmsb {
 namespace tc {
 
+// The fragment-layout epilogue (tcgen05.ld.16x256b, no shared-memory transpose) measures the same as the transposed one;
+// compiling both into the kernels only costs instruction-cache footprint, so it is a build-time option
+// (make EXTRA=-DMMSB_TC_FRAG_EPILOGUE=1, then MMSB_TC_DIRECT=2 selects it).
+#ifndef MMSB_TC_FRAG_EPILOGUE
+#define MMSB_TC_FRAG_EPILOGUE 0
+#endif
+
 constexpr int TM = 128;            // rows of one accumulator (UMMA M)
 constexpr int TK = 32;             // fp32 per k-block = one 128-byte swizzle row
 constexpr int NT = 256;            // widest accumulator (UMMA N)
@@ -539,6 +546,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
     }
     return;
   }
+#if MMSB_TC_FRAG_EPILOGUE
   if (EPI != EPI_ATOMIC && e.direct == 2) {
     // fragment-layout epilogue, software-pipelined: the TMEM reads (and the derivative operand) of the warp's next
     // chunk are in flight while the current one is processed
@@ -584,6 +592,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
     }
     return;
   }
+#endif
   // software pipeline over the warp's chunks: the TMEM read of chunk c + STEP is in flight while chunk c is processed
   uint32_t va[CH], vb[CH];
   tmem_ld16(tmem_acc + uint32_t(first * CH) + (uint32_t(q * 32) << 16), va);
