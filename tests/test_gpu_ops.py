@@ -529,3 +529,60 @@ def test_device_pixel_sampler():
         exp = n / rng
         assert float((counts - exp).abs().max()) < 5.0 * (exp * (1 - 1 / rng)) ** 0.5 + 1
     assert ops.sample_pixels(1, 0, 0, 3, 4, 5, 0, DEV)[0].shape == (0, 3)
+
+
+def test_sdf_net_full_size_row_independence():
+    """BASELINE grid_raw size (2 621 440 SDF rows of one step, 524 288 of them with geometry features): every row's
+    result must not depend on its batch — the full launch equals four row chunks bit for bit — and the parameter
+    gradients are additive over the chunks (split-K atomics: 1e-4 of the largest entry)."""
+    from multimodalstudio_b200 import ops
+    torch.manual_seed(1)
+    n, n_full = 2_621_440, 524_288
+    x = torch.randn(n, 72, device=DEV)[:, :71] * 0.5
+    ws = [torch.randn(256, 71, device=DEV) * 0.1, torch.randn(256, 256, device=DEV) * 0.06, torch.randn(257, 256, device=DEV) * 0.06]
+    bs = [torch.randn(o, device=DEV) * 0.1 for o in (256, 256, 257)]
+    for t in ws + bs:
+        t.requires_grad_(True)
+    g_sdf = torch.randn(n, 1, device=DEV)
+    g_geo = torch.randn(n_full, 256, device=DEV)
+    sdf, geo = ops.sdf_net_forward(x, n_full, ws, bs, "Softplus", 100.0)
+    full = torch.autograd.grad((sdf * g_sdf).sum() + (geo * g_geo).sum(), ws + bs)
+    parts, sdf_parts = None, []
+    bounds = [(0, n_full, n_full), (n_full, n_full + 699_008, 0), (n_full + 699_008, n_full + 2 * 699_008, 0),
+              (n_full + 2 * 699_008, n, 0)]
+    for a, b, nf in bounds:
+        s_c, g_c = ops.sdf_net_forward(x[a:b], nf, ws, bs, "Softplus", 100.0)
+        sdf_parts.append(s_c.detach())
+        loss = (s_c * g_sdf[a:b]).sum() + ((g_c * g_geo).sum() if nf else 0.0)
+        gr = torch.autograd.grad(loss, ws + bs)
+        parts = gr if parts is None else [p + q for p, q in zip(parts, gr)]
+        if nf:
+            assert torch.equal(g_c.detach(), geo.detach())
+    assert torch.equal(torch.cat(sdf_parts), sdf.detach())
+    for a, b, name in zip(full, parts, ["dw0", "dw1", "dw2", "db0", "db1", "db2"]):
+        assert_close(a, b, rtol=1e-4, what=name)
+
+
+def test_hashgrid_backward_linearity_full_size():
+    """2 621 440 look-ups into the 16 x 2^19 x 2 table: the scatter-add is linear in the cotangent
+    (dtable(g1 + g2) = dtable(g1) + dtable(g2), dx likewise) and every table row only receives what its corners send
+    (sum of dtable = sum over look-ups of g, since the 8 corner weights of a look-up sum to 1)."""
+    from multimodalstudio_b200 import ops
+    from multimodalstudio_b200.field_components import HashEncodingConfig
+    torch.manual_seed(2)
+    enc = HashEncodingConfig(num_levels=16, min_res=16, max_res=1024, log2_hashmap_size=19, features_per_level=2,
+                             interpolation="Linear").setup(in_dim=3).to(DEV)
+    desc, tab = enc.desc(1.0), enc.hash_table.detach()
+    n = 2_621_440
+    pts = torch.rand(n, 3, device=DEV) * 2 - 1
+    g1, g2 = torch.randn(n, 32, device=DEV), torch.randn(n, 32, device=DEV)
+    outs = []
+    for g in (g1, g2, g1 + g2):
+        dt, dx = torch.zeros_like(tab), torch.empty(n, 3, device=DEV)
+        ops.hashgrid_bwd_from(desc, pts, tab, None, g, 0, dt, dx)
+        outs.append((dt, dx))
+    assert_close(outs[2][0], outs[0][0] + outs[1][0], rtol=2e-5, what="dtable linearity")
+    assert_close(outs[2][1], outs[0][1] + outs[1][1], rtol=2e-5, atol=1e-6, what="dx linearity")
+    per_level = outs[0][0].reshape(16, -1, 2).sum(1).double()
+    expect = g1.reshape(n, 16, 2).sum(0).double()
+    assert_close(per_level, expect, rtol=1e-4, what="partition of unity")
