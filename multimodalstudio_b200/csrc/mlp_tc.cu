@@ -1164,6 +1164,7 @@ static int launch_rows(const RowsArgs& g_in, cudaStream_t s, const char* what) {
   g.stage_bytes = (NPARTS * (PART + w_max * 128) + 1023) / 1024 * 1024;
   int stages = num_stages(NPARTS) * stage_bytes(NPARTS) / g.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
+  { const char* e = getenv("MMSB_TC_MAX_STAGES"); if (e && atoi(e) >= 2 && stages > atoi(e)) stages = atoi(e); }   // dev
   if (!tma && (stages & 1)) --stages;       // register-staged producers: each of the two groups owns its stages
   g.stages = stages;
   if (tma) return launch_rows_impl<NPARTS, EPI, true>(g, map, s, what);
