@@ -688,6 +688,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g, c
       const int nt = int(tile - mt * g.n_tiles);
       const int w = tile_width(n_pad, nt);
       const uint32_t acc = ti & 1;
+      if (EPI == EPI_DGRAD && g.epi.yprev != nullptr && g.epi.act_prev != MMSB_ACT_NONE) {
+        // the tile's derivative operand (128 rows x w floats) is pulled into the L2 while the tile's MMAs still run
+        const int lines_per_row = (w * 4 + 127) / 128;
+        for (int l = t; l < TM * lines_per_row; l += EPI_WARPS * 32) {
+          const int64_t row = mt * TM + l / lines_per_row;
+          const int col = nt * NT + (l % lines_per_row) * 32;
+          if (row < g.epi.M && col < g.epi.N)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(g.epi.yprev + row * g.epi.ld_yprev + col));
+        }
+      }
       // the derivative operand of this warp's first chunk is requested before the wait on the accumulator
       YPrev y_cur;
       load_yprev<EPI>(g.epi, y_cur, lane, mt * TM + (warp & 3) * 32, nt * NT + (warp >> 2) * CH, vec_y);
