@@ -43,7 +43,7 @@ constexpr int EPI_WARPS = 8, PROD_WARPS = 8;                 // two epilogue war
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int THREADS = (EPI_WARPS + PROD_WARPS + 2) * 32;   // rows kernel: + B-loader warp + MMA warp
 constexpr int WG_STAGE_WARPS = 16;                           // weight-gradient kernel: 2 groups of 8 staging warps
-constexpr int WG_THREADS = (WG_STAGE_WARPS + 1) * 32;        // + MMA warp
+constexpr int WG_THREADS = (WG_STAGE_WARPS + 2) * 32;        // + MMA warp + TMA loader warp
 constexpr int CH = 16;                                       // accumulator columns per epilogue chunk
 constexpr int STG_LD = 20;                                   // floats per row of the epilogue transpose buffer
 constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
@@ -930,17 +930,24 @@ struct WgradArgs {
   int transposed;
 };
 
-template <int NPARTS>
-__global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs g) {
+// TMA: both operands are landed by tensor-map copies (box 32 floats x 32 rows = one MN-major panel,
+// SWIZZLE_128B_ATOM_32B = the UMMA SWIZZLE_128B_BASE32B layout) straight into the stage's hi tiles (the tensor core
+// truncates them to TF32); all 16 staging warps then only derive lo = rna(x - trunc(x)) and the bias sums from shared
+// memory.  Used when both operands have 16-byte aligned rows and dz is a stored operand (not the generated head one).
+template <int NPARTS, bool TMA>
+__global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs g, const __grid_constant__ CUtensorMap tmap_a,
+                                                                 const __grid_constant__ CUtensorMap tmap_b) {
   constexpr int S = num_stages(NPARTS);
   constexpr int STAGE = stage_bytes(NPARTS);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* stg_all = reinterpret_cast<float*>(smem + S * STAGE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * STAGE + STG_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  // barriers: full[4] empty[4] tfull raw[4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
   const uint32_t bar_tfull = smem_u32(bars + 2 * MAX_STAGES);
+  const uint32_t bar_raw = smem_u32(bars + 2 * MAX_STAGES + 4);
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int mt = blockIdx.x / g.n_tiles, nt = blockIdx.x % g.n_tiles;
@@ -954,8 +961,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
 
   if (t == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(bar_full + 8 * s, WG_STAGE_WARPS / 2);       // one arrival per warp of the staging group
+      mbar_init(bar_full + 8 * s, TMA ? WG_STAGE_WARPS : WG_STAGE_WARPS / 2);   // one arrival per staging warp (of the group)
       mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_raw + 8 * s, 1);
     }
     mbar_init(bar_tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -971,7 +979,86 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
   const uint32_t tmem = *tmem_slot;
 
   if (nkb > 0) {
-    if (warp < WG_STAGE_WARPS) {
+    if (TMA && warp < WG_STAGE_WARPS) {
+      // ================= converters: landed raw panels -> lo tiles, bias sums =================
+      const int ca = t & 31, ka = t >> 5;      // dz tile: chunk ca of k-rows ka + 16 i (i < 2)
+      const int cb = t & 63, kbb = t >> 6;     // x tile : chunk cb of k-rows kbb + 8 i (i < 4)
+      const bool b_active = cb < cpr;
+      const bool want_db = g.db != nullptr && nt == 0 && !g.transposed;
+      const bool want_db_b = g.db != nullptr && mt == 0 && g.transposed && b_active;
+      float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f), bsum = colsum;
+      auto lo_of = [](const float4& x) {
+        float4 l;
+        l.x = tf32_rna(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+        l.y = tf32_rna(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+        l.z = tf32_rna(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+        l.w = tf32_rna(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+        return l;
+      };
+      for (int kb = 0; kb < nkb; ++kb) {
+        const uint32_t s = kb % S;
+        mbar_wait(bar_raw + 8 * s, (kb / S) & 1);
+        const uint32_t a_hi = smem_u32(smem + s * STAGE), b_hi = a_hi + NPARTS * PART;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t off = mn_offset(ca, ka + 16 * i);
+          const float4 x = lds128(a_hi + off);
+          colsum.x += x.x; colsum.y += x.y; colsum.z += x.z; colsum.w += x.w;
+          if (NPARTS == 2) sts128(a_hi + PART + off, lo_of(x));
+        }
+        if (b_active) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t off = mn_offset(cb, kbb + 8 * i);
+            const float4 x = lds128(b_hi + off);
+            bsum.x += x.x; bsum.y += x.y; bsum.z += x.z; bsum.w += x.w;
+            if (NPARTS == 2) sts128(b_hi + b_part + off, lo_of(x));
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      }
+      if (want_db) {
+        const int col = m0 + ca * 4;
+        if (col < g.out_dim) atomicAdd(g.db + col, colsum.x);
+        if (col + 1 < g.out_dim) atomicAdd(g.db + col + 1, colsum.y);
+        if (col + 2 < g.out_dim) atomicAdd(g.db + col + 2, colsum.z);
+        if (col + 3 < g.out_dim) atomicAdd(g.db + col + 3, colsum.w);
+      }
+      if (want_db_b) {
+        const int col = n0 + cb * 4;
+        if (col < g.in_dim) atomicAdd(g.db + col, bsum.x);
+        if (col + 1 < g.in_dim) atomicAdd(g.db + col + 1, bsum.y);
+        if (col + 2 < g.in_dim) atomicAdd(g.db + col + 2, bsum.z);
+        if (col + 3 < g.in_dim) atomicAdd(g.db + col + 3, bsum.w);
+      }
+      if (warp < EPI_WARPS) {
+        float* stg = stg_all + warp * 32 * STG_LD;
+        EpiArgs e{};
+        e.C = g.dw; e.ldc = g.lddw; e.M = g.out_dim; e.N = g.in_dim;
+        if (g.transposed) { e.ldc = 1; e.cs = g.lddw; }
+        mbar_wait(bar_tfull, 0);
+        tc_fence_after();
+        YPrev y_none;
+        epilogue_tile<EPI_ATOMIC>(e, tmem, w, stg, warp, lane, m0, n0, false, false, y_none, []() {});
+      }
+    } else if (TMA && warp == WG_STAGE_WARPS + 1) {
+      // ================= loader: one tensor-map copy per 32-wide panel =================
+      if (lane == 0) {
+        const int b_panels = cpr / 8;
+        const uint32_t bytes = uint32_t((TM / 32 + b_panels) * 4096);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint32_t s = kb % S;
+          mbar_wait(bar_empty + 8 * s, ((kb / S) & 1) ^ 1);
+          const uint32_t a_hi = smem_u32(smem + s * STAGE), b_hi = a_hi + NPARTS * PART;
+          const int k0 = int(k_beg + int64_t(kb) * TK);
+          mbar_arrive_expect_tx(bar_raw + 8 * s, bytes);
+          for (int p = 0; p < TM / 32; ++p) tma_load_2d(a_hi + p * 4096, &tmap_a, m0 + 32 * p, k0, bar_raw + 8 * s);
+          for (int p = 0; p < b_panels; ++p) tma_load_2d(b_hi + p * 4096, &tmap_b, n0 + 32 * p, k0, bar_raw + 8 * s);
+        }
+      }
+    } else if (!TMA && warp < WG_STAGE_WARPS) {
       // ================= producers: dz and x rows -> hi/lo -> MN-major swizzled shared memory =================
       // Two groups of eight warps alternate over the k-blocks, each owning its stages (see tc_rows_kernel): the loads
       // of a group's next k-block are in flight while the other group stores and the MMAs of its previous block run.
@@ -1069,7 +1156,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
         YPrev y_none;
         epilogue_tile<EPI_ATOMIC>(e, tmem, w, stg, warp, lane, m0, n0, false, false, y_none, []() {});
       }
-    } else {
+    } else if (warp == WG_STAGE_WARPS) {
       // ================= MMA issuer =================
       if (lane == 0) {
         const uint32_t idesc = make_idesc_tf32(w, true);
@@ -1130,6 +1217,40 @@ static int launch_rows_impl(const RowsArgs& g, const CUtensorMap& map, cudaStrea
   return check_launch(what);
 }
 
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// the driver entry point is resolved through the runtime (no link-time dependency on libcuda: the library must load, and
+// export its symbols, on a machine without a driver)
+static TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn encode = nullptr;
+  static bool resolved = false;
+  if (!resolved) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<TensorMapEncodeFn>(fn);
+    resolved = true;
+  }
+  return encode;
+}
+
+// Tensor map of an MN-major operand of the weight-gradient kernel: [rows, cols] fp32, row stride ld floats, box 32 floats x
+// 32 rows (one panel of a k-block), SWIZZLE_128B_ATOM_32B.
+static bool make_mn_map(const float* p, int64_t ld, int64_t rows, int cols, CUtensorMap* map) {
+  TensorMapEncodeFn encode = tensor_map_encoder();
+  if (encode == nullptr) return false;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) != 0 || (ld & 3) != 0 || rows >= (int64_t(1) << 31)) return false;
+  const cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  const cuuint64_t strides[1] = {cuuint64_t(ld) * sizeof(float)};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Tensor map of the A operand: [M rows, K floats] fp32, row stride lda floats, box 32 floats x 128 rows, SWIZZLE_128B.
 static bool make_a_map(const RowsArgs& g, CUtensorMap* map) {
   static int use_tma = -1;
@@ -1181,17 +1302,32 @@ static int launch_rows(const RowsArgs& g_in, cudaStream_t s, const char* what) {
   return launch_rows_impl<NPARTS, EPI, false>(g, map, s, what);
 }
 
-template <int NPARTS>
-static int launch_wgrad(const WgradArgs& g, dim3 grid, cudaStream_t s, const char* what) {
+template <int NPARTS, bool TMA>
+static int launch_wgrad_impl(const WgradArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, dim3 grid, cudaStream_t s,
+                             const char* what) {
   static bool configured = false;
-  auto kern = tc_wgrad_kernel<NPARTS>;
+  auto kern = tc_wgrad_kernel<NPARTS, TMA>;
   if (!configured) {
     int rc = set_smem(kern, smem_bytes(NPARTS), what);
     if (rc) return rc;
     configured = true;
   }
-  kern<<<grid, WG_THREADS, smem_bytes(NPARTS), s>>>(g);
+  kern<<<grid, WG_THREADS, smem_bytes(NPARTS), s>>>(g, ma, mb);
   return check_launch(what);
+}
+
+template <int NPARTS>
+static int launch_wgrad(const WgradArgs& g, dim3 grid, cudaStream_t s, const char* what) {
+  CUtensorMap ma, mb;
+  memset(&ma, 0, sizeof(ma));
+  memset(&mb, 0, sizeof(mb));
+  static int use_tma = -1;
+  // off by default: measured 12 % slower than the register-staged producers (twelve 4 KB panel copies per k-block)
+  if (use_tma < 0) { const char* e = getenv("MMSB_TC_TMA_WGRAD"); use_tma = e ? atoi(e) : 0; }
+  const bool tma = use_tma && g.hd == nullptr && make_mn_map(g.dz, g.lddz, g.rows, g.out_dim, &ma) &&
+                   make_mn_map(g.x, g.ldx, g.rows, g.in_dim, &mb);
+  if (tma) return launch_wgrad_impl<NPARTS, true>(g, ma, mb, grid, s, what);
+  return launch_wgrad_impl<NPARTS, false>(g, ma, mb, grid, s, what);
 }
 
 }  // namespace tc
