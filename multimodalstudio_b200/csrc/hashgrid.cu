@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_kernel(HashGridParams p, con
 // thread are in flight.
 constexpr int LV = 4;
 
-__global__ void __launch_bounds__(256) hashgrid_fwd4_kernel(HashGridParams p, const float* __restrict__ x, int64_t ldx,
+__global__ void __launch_bounds__(256, 2) hashgrid_fwd4_kernel(HashGridParams p, const float* __restrict__ x, int64_t ldx,
                                                             const float* __restrict__ table,
                                                             const float* __restrict__ mask, float* __restrict__ out,
                                                             int64_t ld_out, int64_t* __restrict__ idx_out, int64_t n) {
