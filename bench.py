@@ -126,6 +126,9 @@ def main():
     ap.add_argument("--all-heads", action="store_true", help="evaluate all M heads for every modality like the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mlp-precision", type=int, default=None, choices=[0, 1, 3],
+                    help="layer arithmetic: 3 = tcgen05 3xTF32 (fp32-accurate, default, the reported configuration), "
+                         "1 = tcgen05 single-pass TF32 (1e-2 band), 0 = fp32 SIMT")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -162,6 +165,11 @@ def main():
     from multimodalstudio_b200.pipelines import RawPipeline, SyntheticScene
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from multimodalstudio_b200 import ops as _ops0
+    if args.mlp_precision is not None:
+        _ops0.set_mlp_precision(args.mlp_precision)
+    cfg_out["layers"] = {0: "fp32 SIMT GEMM", 1: "tcgen05 single-pass TF32 (1e-2 band; not the reported configuration)",
+                         3: "tcgen05 3xTF32, fp32 in / out (1e-5 band)"}[_ops0.MLP_PRECISION]
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
@@ -347,7 +355,7 @@ def main():
     if rank == 0:
         line = {"metric": "train rays/sec (fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": cfg_out, "clocks": clk, "e2e": e2e, "gpu_launches": launches,
+                "dtype": {0: "f32", 1: "tf32", 3: "f32"}[_ops.MLP_PRECISION] if roof else "f32", "data": "synthetic", "config": cfg_out, "clocks": clk, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roof, "roofline_hashgrid": roof_hash, "cpu_baseline": cpu, "inference": inference, "impl": "b200"}
         print(json.dumps(line))
     if world > 1:
