@@ -262,3 +262,50 @@ def test_sdf_volume_matches_oracle():
     with torch.no_grad():
         ref = orc.sdf_field(pts)[0].reshape(12, 12, 12)
     assert_close(vol, ref, rtol=3e-5, atol=1e-6, what="sdf volume")
+
+
+def test_demosaicked_grid_step_matches_oracle():
+    """The `grid` workload of bench.py (demosaicked frames: full [R, C] targets, no mosaick select; RGB + infrared,
+    64 + 64 samples per ray): outputs, loss and parameter gradients of one training step against the CPU oracle."""
+    from multimodalstudio_b200.cameras import RayBundle
+    from multimodalstudio_b200.models import build_model, grid_loss_config
+    mods = {"rgb": 3, "infrared": 1}
+    model = build_model("grid", modalities=mods, log2_hashmap_size=12, seed=4, num_samples=64, num_samples_importance=64,
+                        render_all_heads=False).to(DEV)
+    model.set_schedule_state(16, 2.0 / 1024, 1.0)
+    model.train()
+    gen = torch.Generator().manual_seed(8)
+    n = 40
+    bundles, inputs, rand, targets = {}, {}, {"uniform": {}, "pdf": {}, "background": {}}, {}
+    for mod, c in mods.items():
+        o = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1) * 2.5
+        d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(n, 3, generator=gen), dim=-1)
+        up = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1)
+        inputs[mod] = (o, d, up)
+        bundles[mod] = RayBundle(None, o.to(DEV), d.to(DEV), up.to(DEV))
+        rand["uniform"][mod] = torch.rand(n, 1, generator=gen)
+        rand["pdf"][mod] = [torch.rand(n, 1, generator=gen) for _ in range(4)]
+        rand["background"][mod] = torch.rand(n, 17, generator=gen)
+        targets[mod] = torch.rand(n, c, generator=gen)
+    dr = {k: {m: (v.to(DEV) if torch.is_tensor(v) else [t.to(DEV) for t in v]) for m, v in d_.items()} for k, d_ in rand.items()}
+    outputs = model(bundles, rand=dr)
+    lm = grid_loss_config().setup(modalities=list(mods), num_iterations=100000, model=model)
+    losses, total = lm.compute_loss(outputs, {m: t.to(DEV) for m, t in targets.items()}, None, 60000, mosaick_patterns=None)
+    total.backward()
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    orc = O.GridModelOracle(sd, O.default_cfg(modalities=mods, log2_hashmap_size=12, num_samples=64, num_samples_importance=64))
+    ref_out = {}
+    for mod, (o, d, up) in inputs.items():
+        hit = O.sphere_collide(o, d)[2]
+        r = {"uniform": rand["uniform"][mod][hit], "pdf": [t[hit] for t in rand["pdf"][mod]], "background": rand["background"][mod]}
+        ref_out[mod] = orc.forward_modality(mod, o, d, up, r)
+        # 3xTF32 layers + the CUDA sampler's own bins (see test_train_step_matches_reference, own_sampler=True)
+        assert_close(outputs[mod][mod], ref_out[mod][mod], rtol=6e-3, atol=1e-5, what=f"{mod} colour")
+    _, ref_total = orc.loss(ref_out, targets, None, None, float(losses["curvature_loss_weight"]))
+    assert_close(total, ref_total, rtol=6e-3, what="total loss")
+    ref_total.backward()
+    for k, p in model.named_parameters():
+        if "hash_table" in k or sd[k].grad is None:
+            continue
+        gr = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert_close(gr, sd[k].grad, rtol=6e-2, atol=1e-6, what=k)
