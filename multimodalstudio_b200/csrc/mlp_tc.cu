@@ -914,6 +914,239 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g, c
   }
 }
 
+
+// ---- forward / dgrad on CTA pairs (cta_group::2) ------------------------------------------------------------------
+// Two CTAs of a cluster (two SMs of one TPC) share one 256-row x 256-column tile: each CTA lands and converts the A
+// k-blocks of its own 128 rows, loads ITS HALF of the weight k-block (128 of the 256 rows of W: 32 KB instead of 64 KB),
+// and the leader CTA issues tcgen05.mma.cta_group::2 (M = 256), which reads both CTAs' operand tiles; each CTA's TMEM
+// holds the accumulator of its own 128 rows and its own epilogue warps drain it.  A stage is 64 KB instead of 96 KB, so the
+// ring holds THREE stages: the stage refill latency (~1.9 us against 0.8 us of MMAs per k-block) is what limited the
+// single-CTA kernel with two.  Barriers the MMA thread waits on live in the leader (rank 0): the peer's converter and
+// epilogue warps arrive remotely (shared::cluster address with the peer bit cleared), both CTAs' weight copies
+// (tensor-map copies with .cta_group::2) complete their bytes on the leader's barrier, and the MMA completions are
+// committed with a multicast to both CTAs' barriers.
+constexpr int PAIR_STAGES = 3;
+constexpr int PAIR_STAGE = 2 * PART + 2 * (128 * 128);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even CTA
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(leader_bar & kPeerBitMask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(uint16_t(3))
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+    tc_rows_pair_kernel(const RowsArgs g, const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b) {
+  constexpr int S = PAIR_STAGES;
+  constexpr int STAGE = PAIR_STAGE;
+  constexpr int HB = 128 * 128;                       // bytes of one half (128 rows) of a B part
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* stg_all = reinterpret_cast<float*>(smem + S * STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * STAGE + STG_BYTES);
+  // barriers (same offsets in both CTAs): full[4] empty[4] tfull[2] tempty[2] raw[4]
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * MAX_STAGES), bar_tempty = smem_u32(bars + 2 * MAX_STAGES + 2);
+  const uint32_t bar_raw = smem_u32(bars + 2 * MAX_STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int64_t m_ptiles = (g.M + 2 * TM - 1) / (2 * TM);
+  const int64_t total_ptiles = m_ptiles * g.n_tiles;
+  if (t == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8 * s, 2 * PROD_WARPS + 1);   // both CTAs' converter warps + the leader loader's expect_tx
+      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_raw + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 2 * EPI_WARPS);      // both CTAs' epilogue warps
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int last_ksteps = (g.K - (g.nkb - 1) * TK + 7) / 8;
+  const int64_t my_ptiles = pair < total_ptiles ? (total_ptiles - pair + npairs - 1) / npairs : 0;
+
+  if (warp < EPI_WARPS) {
+    // ================= epilogue (this CTA's 128 rows) =================
+    float* stg = stg_all + warp * 32 * STG_LD;
+    const bool vec_ok = ((g.epi.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.epi.C) & 15) == 0);
+    const bool vec_y = ((g.epi.ld_yprev & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.epi.yprev) & 15) == 0);
+    uint32_t ti = 0;
+    for (int64_t pt = pair; pt < total_ptiles; pt += npairs, ++ti) {
+      const int64_t mt = pt / g.n_tiles;
+      const int nt = int(pt - mt * g.n_tiles);
+      const int64_t m0 = mt * 2 * TM + rank * TM;
+      const uint32_t acc = ti & 1;
+      if (EPI == EPI_DGRAD && g.epi.yprev != nullptr && g.epi.act_prev != MMSB_ACT_NONE) {
+        for (int l = t; l < TM * 8; l += EPI_WARPS * 32) {
+          const int64_t row = m0 + l / 8;
+          const int col = nt * NT + (l % 8) * 32;
+          if (row < g.epi.M && col < g.epi.N)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(g.epi.yprev + row * g.epi.ld_yprev + col));
+        }
+      }
+      YPrev y_cur;
+      load_yprev<EPI>(g.epi, y_cur, lane, m0 + (warp & 3) * 32, nt * NT + (warp >> 2) * CH, vec_y);
+      mbar_wait(bar_tfull + 8 * acc, (ti >> 1) & 1);
+      tc_fence_after();
+      epilogue_tile<EPI>(g.epi, tmem + acc * NT, NT, stg, warp, lane, m0, nt * NT, vec_ok, vec_y, y_cur, [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(bar_tempty + 8 * acc);
+      });
+    }
+  } else if (warp < EPI_WARPS + PROD_WARPS) {
+    // ================= converters (this CTA's 128 rows of A) =================
+    const int p = t - EPI_WARPS * 32;
+    const int64_t iters = my_ptiles * g.nkb;
+    const int c = p & 7, r_base = p >> 3;
+    for (int64_t it = 0; it < iters; ++it) {
+      const uint32_t s = uint32_t(it % S);
+      float hd[4];
+      float4 hw4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g.hd) {
+        const int64_t tl = it / g.nkb;
+        const int kb = int(it - tl * g.nkb);
+        const int64_t m0 = ((pair + tl * npairs) / g.n_tiles) * 2 * TM + rank * TM;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t row = m0 + r_base + 32 * i;
+          hd[i] = row < g.M ? __ldg(g.hd + row) : 0.f;
+        }
+        if (kb * TK + c * 4 < g.K) hw4 = load_cols4(g.hw, kb * TK + c * 4, g.K);
+      }
+      mbar_wait(bar_raw + 8 * s, uint32_t(it / S) & 1);
+      const uint32_t hi = smem_u32(smem + s * STAGE), lo = hi + PART;
+#pragma unroll
+      for (int i = 0; i < PART / (PROD_THREADS * 16); ++i) {
+        uint32_t off = uint32_t(p + i * PROD_THREADS) * 16u;
+        if (g.hd) {
+          const int r = r_base + 32 * i;
+          off = uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4);
+        }
+        float4 x = lds128(hi + off);
+        if (g.hd) {
+          x.x = hd[i] * hw4.x * act_bwd_from_y(x.x, g.hact, g.hact_param);
+          x.y = hd[i] * hw4.y * act_bwd_from_y(x.y, g.hact, g.hact_param);
+          x.z = hd[i] * hw4.z * act_bwd_from_y(x.z, g.hact, g.hact_param);
+          x.w = hd[i] * hw4.w * act_bwd_from_y(x.w, g.hact, g.hact_param);
+          sts128(hi + off, x);
+        }
+        float4 l;
+        l.x = tf32_rna(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+        l.y = tf32_rna(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+        l.z = tf32_rna(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+        l.w = tf32_rna(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+        sts128(lo + off, l);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(bar_full + 8 * s);
+    }
+  } else if (warp == EPI_WARPS + PROD_WARPS) {
+    // ================= loader: this CTA's A k-block and its half of the weight k-block =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t pt = pair; pt < total_ptiles; pt += npairs) {
+        const int64_t mt = pt / g.n_tiles;
+        const int nt = int(pt - mt * g.n_tiles);
+        const int m0 = int(mt * 2 * TM + rank * TM);
+        // rows of the packed weight buffer (32 floats each): n-tile nt, k-block kb = [hi 256 rows][lo 256 rows]
+        const int64_t tile_row0 = int64_t(nt) * NT * g.nkb * 2;
+        for (int kb = 0; kb < g.nkb; ++kb, ++it) {
+          const uint32_t s = it % S;
+          mbar_wait(bar_empty + 8 * s, ((it / S) & 1) ^ 1);
+          const uint32_t a_hi = smem_u32(smem + s * STAGE), b_hi = a_hi + 2 * PART;
+          mbar_arrive_expect_tx(bar_raw + 8 * s, uint32_t(PART));
+          tma_load_2d(a_hi, &tmap_a, kb * TK, m0, bar_raw + 8 * s);
+          if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * s, 4u * HB);     // both CTAs' hi + lo halves
+          const int row_hi = int(tile_row0 + int64_t(kb) * 2 * NT + rank * 128);
+          tma_load_2d_pair(b_hi, &tmap_b, 0, row_hi, bar_full + 8 * s);
+          tma_load_2d_pair(b_hi + HB, &tmap_b, 0, row_hi + NT, bar_full + 8 * s);
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS + PROD_WARPS + 1 && rank == 0) {
+    // ================= MMA issuer (leader CTA) =================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(NT >> 3) << 17) | (uint32_t((2 * TM) >> 4) << 24);
+      uint32_t it = 0, ti = 0;
+      for (int64_t pt = pair; pt < total_ptiles; pt += npairs, ++ti) {
+        const uint32_t acc = ti & 1;
+        mbar_wait(bar_tempty + 8 * acc, ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem + acc * NT;
+        for (int kb = 0; kb < g.nkb; ++kb, ++it) {
+          const uint32_t s = it % S;
+          mbar_wait(bar_full + 8 * s, (it / S) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + s * STAGE), b_hi = a_hi + 2 * PART;
+          const uint64_t dah = make_desc(a_hi, 16, 1024), dal = make_desc(a_hi + PART, 16, 1024);
+          const uint64_t dbh = make_desc(b_hi, 16, 1024), dbl = make_desc(b_hi + HB, 16, 1024);
+          const int ksteps = kb == g.nkb - 1 ? last_ksteps : TK / 8;
+          for (int j = 0; j < ksteps; ++j) {
+            const uint64_t adv = uint64_t(j * 2);
+            umma_tf32_pair(d, dal + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
+            umma_tf32_pair(d, dah + adv, dbl + adv, idesc, 1u);
+            umma_tf32_pair(d, dah + adv, dbh + adv, idesc, 1u);
+          }
+          umma_commit_pair(bar_empty + 8 * s);
+        }
+        umma_commit_pair(bar_tfull + 8 * acc);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
 // ---- weight gradient ------------------------------------------------------------------------------------------
 struct WgradArgs {
   const float* dz; int64_t lddz; int out_dim;
@@ -1283,6 +1516,50 @@ static bool make_a_map(const RowsArgs& g, CUtensorMap* map) {
   return r == CUDA_SUCCESS;
 }
 
+
+// Tensor map over the packed weight buffer seen as rows of 32 floats (128 B, already swizzled by the packer): box = 128
+// rows (one CTA's half of a hi or lo tile).
+static bool make_packed_map(const float* packed, int64_t total_rows, CUtensorMap* map) {
+  TensorMapEncodeFn encode = tensor_map_encoder();
+  if (encode == nullptr || (reinterpret_cast<uintptr_t>(packed) & 15) != 0 || total_rows >= (int64_t(1) << 31)) return false;
+  const cuuint64_t dims[2] = {32, cuuint64_t(total_rows)};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {32, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(packed), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int EPI>
+static int launch_rows_pair(const RowsArgs& g, const CUtensorMap& map_a, cudaStream_t s, const char* what) {
+  CUtensorMap map_b;
+  memset(&map_b, 0, sizeof(map_b));
+  const int64_t total_rows = int64_t(pad16(g.N)) * g.nkb * 2;      // hi + lo rows of every k-block
+  if (!make_packed_map(g.Bp, total_rows, &map_b)) return -1000;    // caller falls back to the single-CTA kernel
+  static bool configured = false;
+  auto kern = tc_rows_pair_kernel<EPI>;
+  const int smem = PAIR_STAGES * PAIR_STAGE + STG_BYTES + 256 + 1024;
+  if (!configured) {
+    int rc = set_smem(kern, smem, what);
+    if (rc) return rc;
+    configured = true;
+  }
+  const int64_t ptiles = ceil_div(g.M, 2 * TM) * g.n_tiles;
+  const int64_t pairs = ptiles < kNumSMs / 2 ? ptiles : kNumSMs / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g, map_a, map_b);
+  if (e != cudaSuccess) {
+    set_error("%s: cluster launch failed: %s", what, cudaGetErrorString(e));
+    return MMSB_E_CUDA;
+  }
+  return check_launch(what);
+}
+
 template <int NPARTS, int EPI>
 static int launch_rows(const RowsArgs& g_in, cudaStream_t s, const char* what) {
   RowsArgs g = g_in;
@@ -1298,6 +1575,15 @@ static int launch_rows(const RowsArgs& g_in, cudaStream_t s, const char* what) {
   { const char* e = getenv("MMSB_TC_MAX_STAGES"); if (e && atoi(e) >= 2 && stages > atoi(e)) stages = atoi(e); }   // dev
   if (!tma && (stages & 1)) --stages;       // register-staged producers: each of the two groups owns its stages
   g.stages = stages;
+  {
+    // CTA pairs (cta_group::2): 3xTF32, TMA-fed operand, every accumulator 256 wide, enough rows to fill the machine
+    static int use_pair = -1;
+    if (use_pair < 0) { const char* e = getenv("MMSB_TC_PAIR"); use_pair = e ? atoi(e) : 0; }
+    if (use_pair && NPARTS == 2 && tma && n_pad % NT == 0 && g.M >= 2 * TM * (kNumSMs / 2) && !g.dbg) {
+      const int rc = launch_rows_pair<EPI>(g, map, s, what);
+      if (rc != -1000) return rc;
+    }
+  }
   if (tma) return launch_rows_impl<NPARTS, EPI, true>(g, map, s, what);
   return launch_rows_impl<NPARTS, EPI, false>(g, map, s, what);
 }
