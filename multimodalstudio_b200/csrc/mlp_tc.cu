@@ -1578,7 +1578,7 @@ static int launch_rows(const RowsArgs& g_in, cudaStream_t s, const char* what) {
   {
     // CTA pairs (cta_group::2): 3xTF32, TMA-fed operand, every accumulator 256 wide, enough rows to fill the machine
     static int use_pair = -1;
-    if (use_pair < 0) { const char* e = getenv("MMSB_TC_PAIR"); use_pair = e ? atoi(e) : 0; }
+    if (use_pair < 0) { const char* e = getenv("MMSB_TC_PAIR"); use_pair = e ? atoi(e) : 1; }
     if (use_pair && NPARTS == 2 && tma && n_pad % NT == 0 && g.M >= 2 * TM * (kNumSMs / 2) && !g.dbg) {
       const int rc = launch_rows_pair<EPI>(g, map, s, what);
       if (rc != -1000) return rc;
