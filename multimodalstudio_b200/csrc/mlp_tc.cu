@@ -1032,7 +1032,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
       load_yprev<EPI>(g.epi, y_cur, lane, m0 + (warp & 3) * 32, nt * NT + (warp >> 2) * CH, vec_y);
       mbar_wait(bar_tfull + 8 * acc, (ti >> 1) & 1);
       tc_fence_after();
-      epilogue_tile<EPI>(g.epi, tmem + acc * NT, NT, stg, warp, lane, m0, nt * NT, vec_ok, vec_y, y_cur, [&]() {
+      EpiArgs e_dbg = g.epi;
+      if (g.dbg & 2) e_dbg.M = 0;
+      epilogue_tile<EPI>(e_dbg, tmem + acc * NT, NT, stg, warp, lane, m0, nt * NT, vec_ok, vec_y, y_cur, [&]() {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(bar_tempty + 8 * acc);
@@ -1126,7 +1128,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
           const uint32_t a_hi = smem_u32(smem + s * STAGE), b_hi = a_hi + 2 * PART;
           const uint64_t dah = make_desc(a_hi, 16, 1024), dal = make_desc(a_hi + PART, 16, 1024);
           const uint64_t dbh = make_desc(b_hi, 16, 1024), dbl = make_desc(b_hi + HB, 16, 1024);
-          const int ksteps = kb == g.nkb - 1 ? last_ksteps : TK / 8;
+          const int ksteps = (g.dbg & 8) ? 0 : (kb == g.nkb - 1 ? last_ksteps : TK / 8);
           for (int j = 0; j < ksteps; ++j) {
             const uint64_t adv = uint64_t(j * 2);
             umma_tf32_pair(d, dal + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
@@ -1579,7 +1581,7 @@ static int launch_rows(const RowsArgs& g_in, cudaStream_t s, const char* what) {
     // CTA pairs (cta_group::2): 3xTF32, TMA-fed operand, every accumulator 256 wide, enough rows to fill the machine
     static int use_pair = -1;
     if (use_pair < 0) { const char* e = getenv("MMSB_TC_PAIR"); use_pair = e ? atoi(e) : 1; }
-    if (use_pair && NPARTS == 2 && tma && n_pad % NT == 0 && g.M >= 2 * TM * (kNumSMs / 2) && !g.dbg) {
+    if (use_pair && NPARTS == 2 && tma && n_pad % NT == 0 && g.M >= 2 * TM * (kNumSMs / 2) && !(g.dbg & 5)) {
       const int rc = launch_rows_pair<EPI>(g, map, s, what);
       if (rc != -1000) return rc;
     }

@@ -8,8 +8,7 @@ x = torch.randn(n, k, device="cuda"); w = torch.randn(o, k, device="cuda") * 0.1
 y = torch.empty(n, o, device="cuda")
 for prec in (3,):
     pw = ops.pack_weight(w, False, prec)
-    for dbg, what in [(0, "full (TMA-fed A)"), (2, "no stores"), (4, "no B copies"), (8, "no MMAs"), (6, "no stores, no B"),
-                      (10, "no stores, no MMAs"), (12, "no B, no MMAs"), (14, "A path + skeleton only"), (1, "register-staged A (full)")]:
+    for dbg, what in [(0, "full (pair kernel)"), (2, "no stores"), (8, "no MMAs"), (10, "no stores, no MMAs")]:
         os.environ["MMSB_TC_DEBUG"] = str(dbg)
         for _ in range(2):
             ops.linear_fwd_tc(x, pw, b, o, 1, 1.0, prec, out=y)
