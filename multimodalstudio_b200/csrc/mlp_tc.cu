@@ -1169,9 +1169,14 @@ struct WgradArgs {
 // SWIZZLE_128B_ATOM_32B = the UMMA SWIZZLE_128B_BASE32B layout) straight into the stage's hi tiles (the tensor core
 // truncates them to TF32); all 16 staging warps then only derive lo = rna(x - trunc(x)) and the bias sums from shared
 // memory.  Used when both operands have 16-byte aligned rows and dz is a stored operand (not the generated head one).
-template <int NPARTS, bool TMA>
+// PAIR: the two 128-row m-tiles of a 256 x 256 weight gradient are the two CTAs of a cluster (blockIdx.x = rank):
+// tcgen05.mma.cta_group::2 (M = 256) issued by rank 0 reads both CTAs' dz tiles and each CTA's HALF of the x tile, so
+// a CTA stages 128 + 128 columns per k-block instead of 128 + 256 (x is no longer staged twice); the peer's staging
+// warps arrive on the leader's barrier, completions are committed to both CTAs (see tc_rows_pair_kernel).
+template <int NPARTS, bool TMA, bool PAIR>
 __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs g, const __grid_constant__ CUtensorMap tmap_a,
                                                                  const __grid_constant__ CUtensorMap tmap_b) {
+  static_assert(!(TMA && PAIR), "the pair variant uses the register-staged producers");
   constexpr int S = num_stages(NPARTS);
   constexpr int STAGE = stage_bytes(NPARTS);
   extern __shared__ uint8_t smem_raw[];
@@ -1188,25 +1193,35 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
   const int mt = blockIdx.x / g.n_tiles, nt = blockIdx.x % g.n_tiles;
   const int m0 = mt * TM, n0 = nt * NT;
   const int w = tile_width(pad16(g.in_dim), nt);       // accumulator width (multiple of 16)
-  const int cpr = (w + 31) / 32 * 8;                   // 16-byte chunks per staged row of x (whole 32-wide panels)
+  // 16-byte chunks per staged row of x (whole 32-wide panels); a pair CTA stages its half of the 256 columns
+  const int cpr = PAIR ? 32 : (w + 31) / 32 * 8;
   const int b_part = cpr * 16 * TK;                    // bytes of one B part: panels x 4096
+  const int xcol0 = PAIR ? n0 + mt * 128 : n0;         // first x column this CTA stages
   const int64_t k_beg = int64_t(blockIdx.y) * g.rows_per_split;
   const int64_t k_end = min(g.rows, k_beg + g.rows_per_split);
   const int nkb = k_beg < k_end ? int((k_end - k_beg + TK - 1) / TK) : 0;
 
   if (t == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(bar_full + 8 * s, TMA ? WG_STAGE_WARPS : WG_STAGE_WARPS / 2);   // one arrival per staging warp (of the group)
+      // one arrival per staging warp (of the group; of both CTAs in a pair)
+      mbar_init(bar_full + 8 * s, TMA ? WG_STAGE_WARPS : (PAIR ? WG_STAGE_WARPS : WG_STAGE_WARPS / 2));
       mbar_init(bar_empty + 8 * s, 1);
       mbar_init(bar_raw + 8 * s, 1);
     }
     mbar_init(bar_tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (PAIR) cluster_sync_all();
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1301,7 +1316,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
       static_assert(S % GROUPS == 0, "a staging group must always meet the same stages");
       const int grp = t >> 8, q = t & 255;
       const int ca = q & 31, ka = q >> 5;      // dz tile: 32 chunks per k-row, k-rows ka + 8 i (i < 4)
-      const int cb = q & 63, kbb = q >> 6;     // x tile : up to 64 chunks per k-row, k-rows kbb + 4 i (i < 8)
+      // x tile: up to 64 chunks per k-row, k-rows kbb + 4 i (i < 8); pair: 32 chunks, k-rows kbb + 8 i (i < 4)
+      const int cb = PAIR ? (q & 31) : (q & 63), kbb = PAIR ? (q >> 5) : (q >> 6);
+      constexpr int NB = PAIR ? 4 : 8, KSTEP_B = PAIR ? 8 : 4;
       const bool vec_a = ((g.lddz & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.dz) & 15) == 0);
       const bool vec_b = ((g.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.x) & 15) == 0);
       const bool b_active = cb < cpr;
@@ -1321,7 +1338,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
         for (int i = 0; i < 4; ++i) va[i] = load4(g.dz, g.lddz, k0 + ka + 8 * i, k_end, m0 + ca * 4, g.out_dim, vec_a);
         if (b_active) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) vb[i] = load4(g.x, g.ldx, k0 + kbb + 4 * i, k_end, n0 + cb * 4, g.in_dim, vec_b);
+          for (int i = 0; i < NB; ++i) vb[i] = load4(g.x, g.ldx, k0 + kbb + KSTEP_B * i, k_end, xcol0 + cb * 4, g.in_dim, vec_b);
         }
       };
       int kb = grp;
@@ -1347,14 +1364,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
         }
         if (b_active) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            split_store4<NPARTS>(b_hi, b_hi + b_part, mn_offset(cb, kbb + 4 * i), vb[i]);
+          for (int i = 0; i < NB; ++i) {
+            split_store4<NPARTS>(b_hi, b_hi + b_part, mn_offset(cb, kbb + KSTEP_B * i), vb[i]);
             bsum.x += vb[i].x; bsum.y += vb[i].y; bsum.z += vb[i].z; bsum.w += vb[i].w;
           }
         }
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full + 8 * s);     // one arrival per warp
+        if (lane == 0) {                                  // one arrival per warp
+          if (PAIR) mbar_arrive_leader(bar_full + 8 * s);
+          else mbar_arrive(bar_full + 8 * s);
+        }
         kb += GROUPS;
         if (kb < nkb) load_block(kb);
       }
@@ -1391,10 +1411,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
         YPrev y_none;
         epilogue_tile<EPI_ATOMIC>(e, tmem, w, stg, warp, lane, m0, n0, false, false, y_none, []() {});
       }
-    } else if (warp == WG_STAGE_WARPS) {
-      // ================= MMA issuer =================
+    } else if (warp == WG_STAGE_WARPS && (!PAIR || mt == 0)) {
+      // ================= MMA issuer (pair: the leader CTA) =================
       if (lane == 0) {
-        const uint32_t idesc = make_idesc_tf32(w, true);
+        uint32_t idesc = make_idesc_tf32(w, true);
+        if (PAIR) idesc = (1u << 4) | (2u << 7) | (2u << 10) | (3u << 15) | (uint32_t(NT >> 3) << 17) | (uint32_t((2 * TM) >> 4) << 24);
         for (int kb = 0; kb < nkb; ++kb) {
           const uint32_t s = kb % S;
           mbar_wait(bar_full + 8 * s, (kb / S) & 1);
@@ -1407,7 +1428,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
 #pragma unroll
           for (int j = 0; j < TK / 8; ++j) {
             const uint64_t adv = uint64_t(j * (1024 >> 4));   // 8 k-rows = one 1024-byte atom
-            if (NPARTS == 2) {
+            if (PAIR) {
+              if (NPARTS == 2) {
+                umma_tf32_pair(tmem, dal + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
+                umma_tf32_pair(tmem, dah + adv, dbl + adv, idesc, 1u);
+                umma_tf32_pair(tmem, dah + adv, dbh + adv, idesc, 1u);
+              } else {
+                umma_tf32_pair(tmem, dah + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
+              }
+            } else if (NPARTS == 2) {
               umma_tf32(tmem, dal + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
               umma_tf32(tmem, dah + adv, dbl + adv, idesc, 1u);
               umma_tf32(tmem, dah + adv, dbh + adv, idesc, 1u);
@@ -1415,16 +1444,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
               umma_tf32(tmem, dah + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
             }
           }
-          umma_commit(bar_empty + 8 * s);
+          if (PAIR) umma_commit_pair(bar_empty + 8 * s);
+          else umma_commit(bar_empty + 8 * s);
         }
-        umma_commit(bar_tfull);
+        if (PAIR) umma_commit_pair(bar_tfull);
+        else umma_commit(bar_tfull);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
   }
 }
 
@@ -1590,15 +1623,35 @@ static int launch_rows(const RowsArgs& g_in, cudaStream_t s, const char* what) {
   return launch_rows_impl<NPARTS, EPI, false>(g, map, s, what);
 }
 
-template <int NPARTS, bool TMA>
+template <int NPARTS, bool TMA, bool PAIR>
 static int launch_wgrad_impl(const WgradArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, dim3 grid, cudaStream_t s,
                              const char* what) {
   static bool configured = false;
-  auto kern = tc_wgrad_kernel<NPARTS, TMA>;
+  auto kern = tc_wgrad_kernel<NPARTS, TMA, PAIR>;
   if (!configured) {
     int rc = set_smem(kern, smem_bytes(NPARTS), what);
     if (rc) return rc;
     configured = true;
+  }
+  if (PAIR) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(WG_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes(NPARTS);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g, ma, mb);
+    if (e != cudaSuccess) {
+      set_error("%s: cluster launch failed: %s", what, cudaGetErrorString(e));
+      return MMSB_E_CUDA;
+    }
+    return check_launch(what);
   }
   kern<<<grid, WG_THREADS, smem_bytes(NPARTS), s>>>(g, ma, mb);
   return check_launch(what);
@@ -1614,8 +1667,13 @@ static int launch_wgrad(const WgradArgs& g, dim3 grid, cudaStream_t s, const cha
   if (use_tma < 0) { const char* e = getenv("MMSB_TC_TMA_WGRAD"); use_tma = e ? atoi(e) : 0; }
   const bool tma = use_tma && g.hd == nullptr && make_mn_map(g.dz, g.lddz, g.rows, g.out_dim, &ma) &&
                    make_mn_map(g.x, g.ldx, g.rows, g.in_dim, &mb);
-  if (tma) return launch_wgrad_impl<NPARTS, true>(g, ma, mb, grid, s, what);
-  return launch_wgrad_impl<NPARTS, false>(g, ma, mb, grid, s, what);
+  if (tma) return launch_wgrad_impl<NPARTS, true, false>(g, ma, mb, grid, s, what);
+  static int use_pair = -1;
+  if (use_pair < 0) { const char* e = getenv("MMSB_TC_PAIR_WGRAD"); use_pair = e ? atoi(e) : 1; }
+  // CTA pair: exactly two m-tiles and one full 256-wide n-tile (grid.x = 2 = the cluster)
+  if (use_pair && !g.transposed && grid.x == 2 && g.n_tiles == 1 && pad16(g.in_dim) == NT && g.out_dim > TM)
+    return launch_wgrad_impl<NPARTS, false, true>(g, ma, mb, grid, s, what);
+  return launch_wgrad_impl<NPARTS, false, false>(g, ma, mb, grid, s, what);
 }
 
 }  // namespace tc
