@@ -30,6 +30,9 @@ namespace tc {
 // The fragment-layout epilogue (tcgen05.ld.16x256b, no shared-memory transpose) measures the same as the transposed one;
 // compiling both into the kernels only costs instruction-cache footprint, so it is a build-time option
 // (make EXTRA=-DMMSB_TC_FRAG_EPILOGUE=1, then MMSB_TC_DIRECT=2 selects it).
+#ifndef MMSB_TC_EPI_ILP
+#define MMSB_TC_EPI_ILP 4
+#endif
 #ifndef MMSB_TC_FRAG_EPILOGUE
 #define MMSB_TC_FRAG_EPILOGUE 0
 #endif
@@ -314,6 +317,14 @@ __device__ __forceinline__ void load_yprev(const EpiArgs& e, YPrev& y, int lane,
   }
   if (e.yprev == nullptr || e.act_prev == MMSB_ACT_NONE) return;
   const int col = col0 + 4 * (lane & 3);
+  if (vec_y && row0 + 32 <= e.M && col0 + CH <= e.N) {
+    // interior chunk (warp-uniform): four independent 16-byte loads, no bounds checks
+    const float* p = e.yprev + (row0 + (lane >> 2)) * e.ld_yprev + col;
+    const int64_t step = 8 * e.ld_yprev;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y.v[i] = __ldg(reinterpret_cast<const float4*>(p + i * step));
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int64_t row = row0 + (lane >> 2) + 8 * i;
@@ -332,9 +343,82 @@ __device__ __forceinline__ float4 load_cols4(const float* __restrict__ p, int co
   return v;
 }
 
-template <int EPI, int ACT>
-__device__ __forceinline__ void epilogue_rows(const EpiArgs& e, const float* stg, const YPrev& yp, int lane, int64_t row0,
-                                              int col0, bool vec_ok, float (&hacc)[4]) {
+// 4 values of a per-column vector at col..col+3, all inside the vector (interior chunks)
+__device__ __forceinline__ float4 load_cols4_in(const float* __restrict__ p, int col) {
+  if (p == nullptr) return make_float4(0.f, 0.f, 0.f, 0.f);
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) return __ldg(reinterpret_cast<const float4*>(p + col));
+  return make_float4(__ldg(p + col), __ldg(p + col + 1), __ldg(p + col + 2), __ldg(p + col + 3));
+}
+
+// Interior chunk (all 32 rows and CH columns inside C, 16-byte aligned rows; the test is warp-uniform): the four rows of
+// a lane are processed as four independent, branch-free dependency chains (shared-memory read -> MUFU -> store), so
+// their latencies overlap; the edge chunks take the bounds-checked path below.
+// per-column vectors of a lane's 4 columns (bias, fused-head weights | rank-1 weights), fetched at the top of the chunk
+// iteration so that their latency is covered by the TMEM wait and the transpose
+struct ColVecs {
+  float4 b4, h4, r4;
+};
+template <int EPI>
+__device__ __forceinline__ void load_colvecs(const EpiArgs& e, ColVecs& cv, int lane, int col0) {
+  const int col = col0 + 4 * (lane & 3);
+  cv.b4 = cv.h4 = cv.r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (EPI == EPI_FWD) {
+    cv.b4 = load_cols4_in(e.bias, col);
+    cv.h4 = load_cols4_in(e.head_w, col);
+  }
+  if (EPI == EPI_DGRAD && e.r1_d) cv.r4 = load_cols4_in(e.r1_w, col);
+}
+
+template <int EPI, int ACT, typename Next>
+__device__ __forceinline__ void epilogue_rows_in(const EpiArgs& e, const float* stg, const YPrev& yp, const ColVecs& cv,
+                                                 int lane, int64_t row0, int col0, float (&hacc)[4], Next issue_next) {
+  const int q4 = lane & 3, r0 = lane >> 2;
+  const int col = col0 + 4 * q4;
+  const float4 b4 = cv.b4, h4 = cv.h4, r4 = cv.r4;
+  // rows in flight per lane (the dgrad kernels also hold two derivative operands: fewer registers left)
+  constexpr int G = EPI == EPI_DGRAD ? MMSB_TC_EPI_ILP / 2 : MMSB_TC_EPI_ILP;
+  const uint32_t src = smem_u32(stg + r0 * STG_LD + 4 * q4);
+  float* dst = e.C ? e.C + (row0 + r0) * e.ldc + col : nullptr;
+  const int64_t step = 8 * e.ldc;
+#pragma unroll
+  for (int i0 = 0; i0 < 4; i0 += G) {
+    float4 x[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) x[j] = lds128(src + uint32_t((i0 + j) * 8 * STG_LD * 4));
+    // the transposing stores have been consumed by now: the accumulator registers can take the next TMEM read without
+    // the read-after-write stall an issue right behind the stores would see
+    if (i0 == 0) issue_next();
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int i = i0 + j;
+      if (EPI == EPI_FWD) {
+        x[j].x += b4.x; x[j].y += b4.y; x[j].z += b4.z; x[j].w += b4.w;
+        x[j] = act_fwd4<ACT>(x[j], e.act_param);
+        if (e.head_w) hacc[i] = fmaf(x[j].x, h4.x, fmaf(x[j].y, h4.y, fmaf(x[j].z, h4.z, fmaf(x[j].w, h4.w, hacc[i]))));
+      } else {
+        if (e.r1_d) {
+          const float d = yp.d[i];
+          x[j].x = fmaf(d, r4.x, x[j].x); x[j].y = fmaf(d, r4.y, x[j].y); x[j].z = fmaf(d, r4.z, x[j].z);
+          x[j].w = fmaf(d, r4.w, x[j].w);
+        }
+        if (ACT != MMSB_ACT_NONE) {
+          const float4 y = act_bwd4<ACT>(yp.v[i], e.act_prev_param);
+          x[j].x *= y.x; x[j].y *= y.y; x[j].z *= y.z; x[j].w *= y.w;
+        }
+      }
+    }
+    if (dst != nullptr) {
+#pragma unroll
+      for (int j = 0; j < G; ++j) *reinterpret_cast<float4*>(dst + (i0 + j) * step) = x[j];
+    }
+  }
+}
+
+// Edge chunks (last rows / columns of C, unaligned rows) and the reducing epilogue: bounds-checked, activation chosen at
+// run time (one copy per kernel: the interior path above is the one that has to be fast).
+template <int EPI>
+__device__ __forceinline__ void epilogue_rows_edge(const EpiArgs& e, const float* stg, const YPrev& yp, int lane, int64_t row0,
+                                                int col0, bool vec_ok, float (&hacc)[4], int ACT) {
   const int q4 = lane & 3;
   const int col = col0 + 4 * q4;
   if (col >= e.N) return;
@@ -354,7 +438,8 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& e, const float* stg
     float* dst = e.C + row * e.ldc + col;
     if (EPI == EPI_FWD) {
       x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-      x = act_fwd4<ACT>(x, e.act_param);
+      x.x = act_fwd(x.x, ACT, e.act_param); x.y = act_fwd(x.y, ACT, e.act_param); x.z = act_fwd(x.z, ACT, e.act_param);
+      x.w = act_fwd(x.w, ACT, e.act_param);
       if (e.head_w) {
         hacc[i] = fmaf(x.x, h4.x, fmaf(x.y, h4.y, fmaf(x.z, h4.z, fmaf(x.w, h4.w, hacc[i]))));
         if (e.C == nullptr) continue;
@@ -365,7 +450,9 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& e, const float* stg
         x.x = fmaf(d, r4.x, x.x); x.y = fmaf(d, r4.y, x.y); x.z = fmaf(d, r4.z, x.z); x.w = fmaf(d, r4.w, x.w);
       }
       if (ACT != MMSB_ACT_NONE) {
-        const float4 y = act_bwd4<ACT>(yp.v[i], e.act_prev_param);
+        float4 y = yp.v[i];
+        y.x = act_bwd_from_y(y.x, ACT, e.act_prev_param); y.y = act_bwd_from_y(y.y, ACT, e.act_prev_param);
+        y.z = act_bwd_from_y(y.z, ACT, e.act_prev_param); y.w = act_bwd_from_y(y.w, ACT, e.act_prev_param);
         x.x *= y.x; x.y *= y.y; x.z *= y.z; x.w *= y.w;
       }
     }
@@ -387,22 +474,39 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& e, const float* stg
   }
 }
 
-// One chunk: lane owns row (row0 + lane) in registers -> transpose buffer -> epilogue_rows.
-template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, uint32_t (&v)[CH], float* stg, const YPrev& yp, int lane,
-                                               int64_t row0, int col0, bool vec_ok, float (&hacc)[4]) {
+// One chunk, part 1: lane owns row (row0 + lane) of the accumulator in registers -> transpose buffer.  The registers are
+// free again afterwards (the TMEM read of the warp's next chunk is issued into them while this chunk is processed).
+__device__ __forceinline__ void epilogue_stage(const uint32_t (&v)[CH], float* stg, int lane) {
 #pragma unroll
   for (int j = 0; j < CH / 4; ++j)
     sts128(smem_u32(stg + lane * STG_LD + 4 * j),
            make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                        __uint_as_float(v[4 * j + 3])));
+}
+// Part 2: transpose buffer -> bias / activation / derivative -> global rows.
+// interior chunk (warp-uniform test); Sigmoid (output layers only, a few columns wide) always takes the edge path
+template <int EPI>
+__device__ __forceinline__ bool chunk_is_interior(const EpiArgs& e, int64_t row0, int col0, bool vec_ok, int act) {
+  return EPI != EPI_ATOMIC && vec_ok && row0 + 32 <= e.M && col0 + CH <= e.N && act != MMSB_ACT_SIGMOID;
+}
+template <int EPI>
+__device__ __forceinline__ int chunk_act(const EpiArgs& e) {
+  return EPI == EPI_FWD ? e.act : (EPI == EPI_DGRAD && e.yprev ? e.act_prev : MMSB_ACT_NONE);
+}
+template <int EPI, typename Next>
+__device__ __forceinline__ void epilogue_chunk_rows(const EpiArgs& e, float* stg, const YPrev& yp, const ColVecs& cv,
+                                                    bool interior, int act, int lane, int64_t row0, int col0, bool vec_ok,
+                                                    float (&hacc)[4], Next issue_next) {
   __syncwarp();
-  const int act = EPI == EPI_FWD ? e.act : (EPI == EPI_DGRAD && e.yprev ? e.act_prev : MMSB_ACT_NONE);
-  switch (act) {
-    case MMSB_ACT_RELU: epilogue_rows<EPI, MMSB_ACT_RELU>(e, stg, yp, lane, row0, col0, vec_ok, hacc); break;
-    case MMSB_ACT_SOFTPLUS: epilogue_rows<EPI, MMSB_ACT_SOFTPLUS>(e, stg, yp, lane, row0, col0, vec_ok, hacc); break;
-    case MMSB_ACT_SIGMOID: epilogue_rows<EPI, MMSB_ACT_SIGMOID>(e, stg, yp, lane, row0, col0, vec_ok, hacc); break;
-    default: epilogue_rows<EPI, MMSB_ACT_NONE>(e, stg, yp, lane, row0, col0, vec_ok, hacc); break;
+  if (interior) {
+    switch (act) {
+      case MMSB_ACT_RELU: epilogue_rows_in<EPI, MMSB_ACT_RELU>(e, stg, yp, cv, lane, row0, col0, hacc, issue_next); break;
+      case MMSB_ACT_SOFTPLUS: epilogue_rows_in<EPI, MMSB_ACT_SOFTPLUS>(e, stg, yp, cv, lane, row0, col0, hacc, issue_next); break;
+      default: epilogue_rows_in<EPI, MMSB_ACT_NONE>(e, stg, yp, cv, lane, row0, col0, hacc, issue_next); break;
+    }
+  } else {
+    issue_next();
+    epilogue_rows_edge<EPI>(e, stg, yp, lane, row0, col0, vec_ok, hacc, act);
   }
   __syncwarp();
 }
@@ -532,20 +636,6 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
     release();
     return;
   }
-  if constexpr (EPI == EPI_DGRAD) {
-    // the derivative operand of the next chunk is what is kept in flight here (registers do not allow both)
-    for (int c = first; c < nch; c += STEP) {
-      uint32_t v[CH];
-      tmem_ld16(tmem_acc + uint32_t(c * CH) + (uint32_t(q * 32) << 16), v);
-      tmem_ld_wait();
-      if (c + STEP >= nch) release();
-      YPrev y_next;
-      if (c + STEP < nch) load_yprev<EPI>(e, y_next, lane, row0, col_base + (c + STEP) * CH, vec_y);
-      epilogue_chunk<EPI>(e, v, stg, y_cur, lane, row0, col_base + c * CH, vec_ok, hacc);
-      if (c + STEP < nch) y_cur = y_next;
-    }
-    return;
-  }
 #if MMSB_TC_FRAG_EPILOGUE
   if (EPI != EPI_ATOMIC && e.direct == 2) {
     // fragment-layout epilogue, software-pipelined: the TMEM reads (and the derivative operand) of the warp's next
@@ -593,25 +683,31 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
     return;
   }
 #endif
-  // software pipeline over the warp's chunks: the TMEM read of chunk c + STEP is in flight while chunk c is processed
-  uint32_t va[CH], vb[CH];
-  tmem_ld16(tmem_acc + uint32_t(first * CH) + (uint32_t(q * 32) << 16), va);
-  for (int c = first; c < nch; c += 2 * STEP) {
-    const int c1 = c + STEP, c2 = c + 2 * STEP;
+  // software pipeline over the warp's chunks with ONE register array: chunk c is moved to the transpose buffer, then the
+  // TMEM read of chunk c + STEP (and, dgrad, its derivative operand) is issued and stays in flight while chunk c is
+  // processed from shared memory.  One call site, loop not unrolled: the code of the activation variants exists once.
+  // (dgrad: the derivative operand of the next chunk is what is kept in flight, the registers do not allow both)
+  constexpr bool LD_AHEAD = EPI != EPI_DGRAD;
+  uint32_t v[CH];
+  if (LD_AHEAD) tmem_ld16(tmem_acc + uint32_t(first * CH) + (uint32_t(q * 32) << 16), v);
+  const int act = chunk_act<EPI>(e);
+#pragma unroll 1
+  for (int c = first; c < nch; c += STEP) {
+    const int cn = c + STEP;
+    if (!LD_AHEAD) tmem_ld16(tmem_acc + uint32_t(c * CH) + (uint32_t(q * 32) << 16), v);
+    const bool interior = chunk_is_interior<EPI>(e, row0, col_base + c * CH, vec_ok, act);
+    ColVecs cv;
+    if (interior && EPI != EPI_DGRAD) load_colvecs<EPI>(e, cv, lane, col_base + c * CH);
     tmem_ld_wait();
-    if (c1 < nch) tmem_ld16(tmem_acc + uint32_t(c1 * CH) + (uint32_t(q * 32) << 16), vb);
-    else release();
+    epilogue_stage(v, stg, lane);
+    if (cn >= nch) release();
+    if (interior && EPI == EPI_DGRAD) load_colvecs<EPI>(e, cv, lane, col_base + c * CH);   // (no registers to spare earlier)
     YPrev y_next;
-    if (c1 < nch) load_yprev<EPI>(e, y_next, lane, row0, col_base + c1 * CH, vec_y);
-    epilogue_chunk<EPI>(e, va, stg, y_cur, lane, row0, col_base + c * CH, vec_ok, hacc);
-    if (c1 >= nch) break;
-    y_cur = y_next;
-    tmem_ld_wait();
-    if (c2 < nch) tmem_ld16(tmem_acc + uint32_t(c2 * CH) + (uint32_t(q * 32) << 16), va);
-    else release();
-    if (c2 < nch) load_yprev<EPI>(e, y_next, lane, row0, col_base + c2 * CH, vec_y);
-    epilogue_chunk<EPI>(e, vb, stg, y_cur, lane, row0, col_base + c1 * CH, vec_ok, hacc);
-    if (c2 < nch) y_cur = y_next;
+    if (cn < nch) load_yprev<EPI>(e, y_next, lane, row0, col_base + cn * CH, vec_y);
+    epilogue_chunk_rows<EPI>(e, stg, y_cur, cv, interior, act, lane, row0, col_base + c * CH, vec_ok, hacc, [&]() {
+      if (LD_AHEAD && cn < nch) tmem_ld16(tmem_acc + uint32_t(cn * CH) + (uint32_t(q * 32) << 16), v);
+    });
+    if (EPI == EPI_DGRAD && cn < nch) y_cur = y_next;
   }
   head_flush();
 }
@@ -635,7 +731,7 @@ struct RowsArgs {
 // load sits in a register (or on the hand-shake path) any more.  Needs 16-byte aligned rows of A and a stored operand;
 // otherwise (generated operand, odd leading dimension) the register-staged producers below are used.
 template <int NPARTS, int EPI, bool TMA_A>
-__global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g, const __grid_constant__ CUtensorMap tmap_a) {
+__global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const __grid_constant__ RowsArgs g, const __grid_constant__ CUtensorMap tmap_a) {
   // stages: as many as fit into the ring (2 x 96 KB) for this launch's widest B tile — 2 for a 256-wide accumulator,
   // 3..4 for narrow layers (their MMAs are short, so the stage refill latency is what a deeper ring hides)
   constexpr int RING = num_stages(NPARTS) * stage_bytes(NPARTS);
@@ -703,14 +799,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const RowsArgs g, c
       load_yprev<EPI>(g.epi, y_cur, lane, mt * TM + (warp & 3) * 32, nt * NT + (warp >> 2) * CH, vec_y);
       mbar_wait(bar_tfull + 8 * acc, (ti >> 1) & 1);
       tc_fence_after();
-      EpiArgs e_dbg = g.epi;
-      if (g.dbg & 2) e_dbg.M = 0;
-      epilogue_tile<EPI>(e_dbg, tmem + acc * NT, w, stg, warp, lane, mt * TM, nt * NT, vec_ok, vec_y, y_cur, [&]() {
+      auto release = [&]() {
         // one arrival per warp: 256 single-thread arrivals on one mbarrier serialise in the shared-memory atomics
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-      });
+      };
+      if (g.dbg & 2) release();   // dev: no epilogue work
+      else epilogue_tile<EPI>(g.epi, tmem + acc * NT, w, stg, warp, lane, mt * TM, nt * NT, vec_ok, vec_y, y_cur, release);
     }
   } else if (warp < EPI_WARPS + PROD_WARPS) {
     if constexpr (TMA_A) {
@@ -965,7 +1061,7 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, 
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-    tc_rows_pair_kernel(const RowsArgs g, const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b) {
+    tc_rows_pair_kernel(const __grid_constant__ RowsArgs g, const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b) {
   constexpr int S = PAIR_STAGES;
   constexpr int STAGE = PAIR_STAGE;
   constexpr int HB = 128 * 128;                       // bytes of one half (128 rows) of a B part
@@ -1032,13 +1128,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
       load_yprev<EPI>(g.epi, y_cur, lane, m0 + (warp & 3) * 32, nt * NT + (warp >> 2) * CH, vec_y);
       mbar_wait(bar_tfull + 8 * acc, (ti >> 1) & 1);
       tc_fence_after();
-      EpiArgs e_dbg = g.epi;
-      if (g.dbg & 2) e_dbg.M = 0;
-      epilogue_tile<EPI>(e_dbg, tmem + acc * NT, NT, stg, warp, lane, m0, nt * NT, vec_ok, vec_y, y_cur, [&]() {
+      auto release = [&]() {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(bar_tempty + 8 * acc);
-      });
+      };
+      if (g.dbg & 2) release();   // dev: no epilogue work
+      else epilogue_tile<EPI>(g.epi, tmem + acc * NT, NT, stg, warp, lane, m0, nt * NT, vec_ok, vec_y, y_cur, release);
     }
   } else if (warp < EPI_WARPS + PROD_WARPS) {
     // ================= converters (this CTA's 128 rows of A) =================
