@@ -30,6 +30,9 @@ namespace tc {
 // The fragment-layout epilogue (tcgen05.ld.16x256b, no shared-memory transpose) measures the same as the transposed one;
 // compiling both into the kernels only costs instruction-cache footprint, so it is a build-time option
 // (make EXTRA=-DMMSB_TC_FRAG_EPILOGUE=1, then MMSB_TC_DIRECT=2 selects it).
+#ifndef MMSB_TC_EPI_WARPS
+#define MMSB_TC_EPI_WARPS 8
+#endif
 #ifndef MMSB_TC_EPI_ILP
 #define MMSB_TC_EPI_ILP 4
 #endif
@@ -42,7 +45,7 @@ constexpr int TK = 32;             // fp32 per k-block = one 128-byte swizzle ro
 constexpr int NT = 256;            // widest accumulator (UMMA N)
 constexpr int PART = TM * 128;     // bytes of one A part (hi or lo) of a stage
 constexpr int BPART = NT * 128;    // bytes reserved for one B part of a stage
-constexpr int EPI_WARPS = 8, PROD_WARPS = 8;                 // two epilogue warps per TMEM lane quadrant; 2 producer groups
+constexpr int EPI_WARPS = MMSB_TC_EPI_WARPS, PROD_WARPS = 8;   // epilogue warps: a multiple of 4 (TMEM lane quadrants); 2 producer groups
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int THREADS = (EPI_WARPS + PROD_WARPS + 2) * 32;   // rows kernel: + B-loader warp + MMA warp
 constexpr int WG_STAGE_WARPS = 16;                           // weight-gradient kernel: 2 groups of 8 staging warps
@@ -111,6 +114,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
                "l"(map), "r"(k0), "r"(m0), "r"(bar)
                : "memory");
+}
+// L2 prefetch of one tensor-map box (no shared memory, no barrier): issued one tile ahead of the copies so that the
+// ring's refill latency is an L2 hit instead of an HBM access (the ring alone keeps too few bytes in flight per SM)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int k0, int m0) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(k0), "r"(m0) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -712,6 +720,38 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
   head_flush();
 }
 
+// Converter step of one landed A k-block (TMA path): this thread's four 16-byte chunks.  All shared-memory reads are
+// issued before the first dependent instruction (the accesses are volatile asm: the compiler keeps their order), so a
+// k-block costs one shared-memory latency instead of four.
+template <int NPARTS>
+__device__ __forceinline__ void convert_block(uint32_t hi, uint32_t lo, const uint32_t (&off)[4], bool gen, const float (&hd)[4],
+                                              const float4& hw4, int hact, float hact_param) {
+  float4 x[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = lds128(hi + off[i]);
+  if (gen) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      x[i].x = hd[i] * hw4.x * act_bwd_from_y(x[i].x, hact, hact_param);
+      x[i].y = hd[i] * hw4.y * act_bwd_from_y(x[i].y, hact, hact_param);
+      x[i].z = hd[i] * hw4.z * act_bwd_from_y(x[i].z, hact, hact_param);
+      x[i].w = hd[i] * hw4.w * act_bwd_from_y(x[i].w, hact, hact_param);
+      sts128(hi + off[i], x[i]);
+    }
+  }
+  if (NPARTS == 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 l;
+      l.x = tf32_rna(x[i].x - __uint_as_float(__float_as_uint(x[i].x) & 0xFFFFE000u));
+      l.y = tf32_rna(x[i].y - __uint_as_float(__float_as_uint(x[i].y) & 0xFFFFE000u));
+      l.z = tf32_rna(x[i].z - __uint_as_float(__float_as_uint(x[i].z) & 0xFFFFE000u));
+      l.w = tf32_rna(x[i].w - __uint_as_float(__float_as_uint(x[i].w) & 0xFFFFE000u));
+      sts128(lo + off[i], l);
+    }
+  }
+}
+
 // ---- forward / dgrad ----------------------------------------------------------------------------------------
 struct RowsArgs {
   const float* A; int64_t lda; int64_t M; int K;
@@ -723,6 +763,7 @@ struct RowsArgs {
   // activations of the layer
   const float* hd; const float* hw; int hact; float hact_param;
   int stages, stage_bytes;   // ring geometry of this launch (set by launch_rows)
+  int prefetch;              // TMA path: L2 prefetch of the A boxes one tile ahead (MMSB_TC_PREFETCH=1; measured: no gain, off)
 };
 
 // TMA_A: the A k-blocks are landed by tensor-map copies straight into the stage's "hi" tile (K-major SWIZZLE_128B); the
@@ -835,30 +876,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const __grid_consta
           }
           mbar_wait(bar_raw + 8 * s, uint32_t(it / S) & 1);
           const uint32_t hi = smem_u32(smem + s * STAGE), lo = hi + PART;
+          static_assert(PART / (PROD_THREADS * 16) == 4, "four chunks per converter thread");
+          uint32_t off[4];
 #pragma unroll
-          for (int i = 0; i < PART / (PROD_THREADS * 16); ++i) {
-            uint32_t off = uint32_t(p + i * PROD_THREADS) * 16u;     // plain conversion is element-wise: any mapping works
+          for (int i = 0; i < 4; ++i) {
+            off[i] = uint32_t(p + i * PROD_THREADS) * 16u;     // plain conversion is element-wise: any mapping works
             if (g.hd) {
               const int r = r_base + 32 * i;
-              off = uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4);
-            }
-            float4 x = lds128(hi + off);
-            if (g.hd) {
-              x.x = hd[i] * hw4.x * act_bwd_from_y(x.x, g.hact, g.hact_param);
-              x.y = hd[i] * hw4.y * act_bwd_from_y(x.y, g.hact, g.hact_param);
-              x.z = hd[i] * hw4.z * act_bwd_from_y(x.z, g.hact, g.hact_param);
-              x.w = hd[i] * hw4.w * act_bwd_from_y(x.w, g.hact, g.hact_param);
-              sts128(hi + off, x);
-            }
-            if (NPARTS == 2) {
-              float4 l;
-              l.x = tf32_rna(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
-              l.y = tf32_rna(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
-              l.z = tf32_rna(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
-              l.w = tf32_rna(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
-              sts128(lo + off, l);
+              off[i] = uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4);
             }
           }
+          convert_block<NPARTS>(hi, lo, off, g.hd != nullptr, hd, hw4, g.hact, g.hact_param);
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_full + 8 * s);
@@ -934,6 +962,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const __grid_consta
   } else if (warp == EPI_WARPS + PROD_WARPS) {
     // ================= B loader: one bulk async copy per k-block =================
     if (lane == 0) {
+      const bool pf = g.prefetch != 0;
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
         const int nt = int(tile % g.n_tiles);
@@ -951,6 +980,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const __grid_consta
             if (conv) mbar_arrive_expect_tx(a_bar, uint32_t(PART));
             else mbar_arrive_expect_tx(a_bar, uint32_t(PART) + ((g.dbg & 4) ? 0u : bytes));
             tma_load_2d(smem_u32(smem + s * STAGE), &tmap_a, kb * TK, m0, a_bar);
+            if (pf && tile + gridDim.x < g.total_tiles)
+              tma_prefetch_2d(&tmap_a, kb * TK, int(((tile + gridDim.x) / g.n_tiles) * TM));
             if (!conv) {
               if (!(g.dbg & 4))
                 bulk_g2s(smem_u32(smem + s * STAGE + NPARTS * PART), src + int64_t(kb) * NPARTS * w * TK, bytes, a_bar);
@@ -1158,28 +1189,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
       }
       mbar_wait(bar_raw + 8 * s, uint32_t(it / S) & 1);
       const uint32_t hi = smem_u32(smem + s * STAGE), lo = hi + PART;
+      uint32_t off[4];
 #pragma unroll
-      for (int i = 0; i < PART / (PROD_THREADS * 16); ++i) {
-        uint32_t off = uint32_t(p + i * PROD_THREADS) * 16u;
+      for (int i = 0; i < 4; ++i) {
+        off[i] = uint32_t(p + i * PROD_THREADS) * 16u;
         if (g.hd) {
           const int r = r_base + 32 * i;
-          off = uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4);
+          off[i] = uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4);
         }
-        float4 x = lds128(hi + off);
-        if (g.hd) {
-          x.x = hd[i] * hw4.x * act_bwd_from_y(x.x, g.hact, g.hact_param);
-          x.y = hd[i] * hw4.y * act_bwd_from_y(x.y, g.hact, g.hact_param);
-          x.z = hd[i] * hw4.z * act_bwd_from_y(x.z, g.hact, g.hact_param);
-          x.w = hd[i] * hw4.w * act_bwd_from_y(x.w, g.hact, g.hact_param);
-          sts128(hi + off, x);
-        }
-        float4 l;
-        l.x = tf32_rna(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
-        l.y = tf32_rna(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
-        l.z = tf32_rna(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
-        l.w = tf32_rna(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
-        sts128(lo + off, l);
       }
+      convert_block<2>(hi, lo, off, g.hd != nullptr, hd, hw4, g.hact, g.hact_param);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(bar_full + 8 * s);
@@ -1187,6 +1206,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
   } else if (warp == EPI_WARPS + PROD_WARPS) {
     // ================= loader: this CTA's A k-block and its half of the weight k-block =================
     if (lane == 0) {
+      const bool pf = g.prefetch != 0;
       uint32_t it = 0;
       for (int64_t pt = pair; pt < total_ptiles; pt += npairs) {
         const int64_t mt = pt / g.n_tiles;
@@ -1200,6 +1220,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
           const uint32_t a_hi = smem_u32(smem + s * STAGE), b_hi = a_hi + 2 * PART;
           mbar_arrive_expect_tx(bar_raw + 8 * s, uint32_t(PART));
           tma_load_2d(a_hi, &tmap_a, kb * TK, m0, bar_raw + 8 * s);
+          if (pf && pt + npairs < total_ptiles)
+            tma_prefetch_2d(&tmap_a, kb * TK, int(((pt + npairs) / g.n_tiles) * 2 * TM + rank * TM));
           if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * s, 4u * HB);     // both CTAs' hi + lo halves
           const int row_hi = int(tile_row0 + int64_t(kb) * 2 * NT + rank * 128);
           tma_load_2d_pair(b_hi, &tmap_b, 0, row_hi, bar_full + 8 * s);
@@ -1817,6 +1839,7 @@ static int rows_fwd(const float* x, int64_t ldx, const float* packed_w, const fl
   g.n_tiles = int(ceil_div(tc::pad16(out_dim), tc::NT)); g.nkb = int(ceil_div(in_dim, tc::TK));
   g.total_tiles = ceil_div(n, tc::TM) * g.n_tiles;
   { const char* e = getenv("MMSB_TC_DEBUG"); g.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("MMSB_TC_PREFETCH"); g.prefetch = e ? atoi(e) : 0; }
   return precision == 3 ? tc::launch_rows<2, tc::EPI_FWD>(g, stream, what) : tc::launch_rows<1, tc::EPI_FWD>(g, stream, what);
 }
 
@@ -1833,6 +1856,8 @@ static int rows_dgrad(const float* a, int64_t lda, const float* packed_wt, float
   g.hd = hd; g.hw = hw; g.hact = hact; g.hact_param = hact_param;
   g.n_tiles = int(ceil_div(tc::pad16(in_dim), tc::NT)); g.nkb = int(ceil_div(out_dim, tc::TK));
   g.total_tiles = ceil_div(n, tc::TM) * g.n_tiles;
+  { const char* e = getenv("MMSB_TC_DEBUG"); g.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("MMSB_TC_PREFETCH"); g.prefetch = e ? atoi(e) : 0; }
   return precision == 3 ? tc::launch_rows<2, tc::EPI_DGRAD>(g, stream, what) : tc::launch_rows<1, tc::EPI_DGRAD>(g, stream, what);
 }
 
