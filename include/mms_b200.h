@@ -117,6 +117,11 @@ int mmsb_linear_fwd(const float* x, int64_t ldx, const float* w, const float* b,
 /* dz = dy * act'(y)  (in place allowed: dz == dy).  y is the layer OUTPUT (post-activation). */
 int mmsb_act_bwd(const float* dy, int64_t lddy, const float* y, int64_t ldy, float* dz, int64_t lddz,
                  int64_t n, int32_t dim, int32_t act, float act_param, mmsb_stream_t stream);
+/* dst[r, 0:width] = src[r, 0:width], both row-strided (lds, ldd in floats): places an already materialised tensor
+ * (e.g. the geometry features, surface_model.py:124-127 -> radiance_field.py:90-101 `torch.cat`) into its column range
+ * of an assembled MLP input row. */
+int mmsb_copy_rows(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t n, int32_t width,
+                   mmsb_stream_t stream);
 /* dx = dz W  ([n,out] x [out,in]); if y_prev != NULL the previous layer's activation derivative is
  * fused into the epilogue: dx *= act_prev'(y_prev) (y_prev: [n, in] with stride ld_yprev). */
 int mmsb_linear_bwd_data(const float* dz, int64_t lddz, const float* w, float* dx, int64_t lddx,

@@ -265,6 +265,43 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
   dz[row * lddz + c] = __ldg(dy + row * lddy + c) * act_bwd_from_y(__ldg(y + row * ldy + c), act, p);
 }
 
+// 16 bytes per thread when all three operands have 16-byte aligned rows and dim % 4 == 0 (the padded rows of the
+// pipeline): the kernel is a pure HBM stream (12 B per element)
+__global__ void __launch_bounds__(256) act_bwd4_kernel(const float* __restrict__ dy, int64_t lddy,
+                                                       const float* __restrict__ y, int64_t ldy, float* __restrict__ dz,
+                                                       int64_t lddz, int64_t n, int dim4, int act, float p) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n * dim4) return;
+  const int64_t row = t / dim4;
+  const int c = int(t - row * dim4) * 4;
+  const float4 g = __ldg(reinterpret_cast<const float4*>(dy + row * lddy + c));
+  const float4 v = __ldg(reinterpret_cast<const float4*>(y + row * ldy + c));
+  float4 o;
+  o.x = g.x * act_bwd_from_y(v.x, act, p); o.y = g.y * act_bwd_from_y(v.y, act, p);
+  o.z = g.z * act_bwd_from_y(v.z, act, p); o.w = g.w * act_bwd_from_y(v.w, act, p);
+  *reinterpret_cast<float4*>(dz + row * lddz + c) = o;
+}
+
+// dst[r, 0:w] = src[r, 0:w] for row-strided operands (the "copy" pieces of an assembled MLP input row)
+__global__ void __launch_bounds__(256) copy_rows4_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst,
+                                                         int64_t ldd, int64_t n, int w4) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n * w4) return;
+  const int64_t row = t / w4;
+  const int c = int(t - row * w4) * 4;
+  *reinterpret_cast<float4*>(dst + row * ldd + c) = __ldg(reinterpret_cast<const float4*>(src + row * lds + c));
+}
+__global__ void __launch_bounds__(256) copy_rows_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst,
+                                                        int64_t ldd, int64_t n, int w) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n * w) return;
+  const int64_t row = t / w;
+  const int c = int(t - row * w);
+  dst[row * ldd + c] = __ldg(src + row * lds + c);
+}
+
+static __host__ bool aligned16(const void* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld & 3) == 0; }
+
 }  // namespace mmsb
 
 using namespace mmsb;
@@ -301,9 +338,26 @@ extern "C" int mmsb_act_bwd(const float* dy, int64_t lddy, const float* y, int64
   MMSB_REQUIRE(valid_act(act), "act_bwd: unknown activation %d", act);
   if (n == 0) return MMSB_OK;
   MMSB_REQUIRE(dy && y && dz, "act_bwd: NULL pointer");
+  if ((dim & 3) == 0 && aligned16(dy, lddy) && aligned16(y, ldy) && aligned16(dz, lddz)) {
+    act_bwd4_kernel<<<(unsigned)ceil_div(n * (dim / 4), 256), 256, 0, as_stream(stream)>>>(dy, lddy, y, ldy, dz, lddz, n,
+                                                                                          dim / 4, act, act_param);
+    return check_launch("act_bwd");
+  }
   act_bwd_kernel<<<(unsigned)ceil_div(n * dim, 256), 256, 0, as_stream(stream)>>>(dy, lddy, y, ldy, dz, lddz, n, dim,
                                                                                   act, act_param);
   return check_launch("act_bwd");
+}
+
+extern "C" int mmsb_copy_rows(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t n, int32_t width,
+                              mmsb_stream_t stream) {
+  MMSB_REQUIRE(n >= 0 && width >= 1 && lds >= width && ldd >= width, "copy_rows: bad sizes");
+  if (n == 0) return MMSB_OK;
+  MMSB_REQUIRE(src && dst, "copy_rows: NULL pointer");
+  if ((width & 3) == 0 && aligned16(src, lds) && aligned16(dst, ldd))
+    copy_rows4_kernel<<<(unsigned)ceil_div(n * (width / 4), 256), 256, 0, as_stream(stream)>>>(src, lds, dst, ldd, n, width / 4);
+  else
+    copy_rows_kernel<<<(unsigned)ceil_div(n * width, 256), 256, 0, as_stream(stream)>>>(src, lds, dst, ldd, n, width);
+  return check_launch("copy_rows");
 }
 
 extern "C" int mmsb_linear_bwd_data(const float* dz, int64_t lddz, const float* w, float* dx, int64_t lddx,

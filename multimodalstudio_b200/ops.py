@@ -269,7 +269,9 @@ class AssembleFn(torch.autograd.Function):
         saved, col = {}, 0
         for p, w in zip(spec, widths):
             if p[0] == "copy":
-                out[:, col:col + w].copy_(tensors[p[1]].reshape(n, w))
+                src = _rows(tensors[p[1]].reshape(n, w), w)
+                call("mmsb_copy_rows", ptr(src), _i64(src.stride(0)), ptr(out[:, col:]), _i64(out.stride(0)), _i64(n),
+                     _i32(w), stream_ptr())
             elif p[0] == "nerf":
                 x2 = saved.setdefault(p[1], _rows(tensors[p[1]], tensors[p[1]].shape[-1]))
                 nerf_fwd_into(x2, list(p[2]), p[3], out, col)
