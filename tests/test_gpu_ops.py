@@ -447,6 +447,57 @@ def test_tc_layer_products_vs_fp64(prec, tol, n, k, o):
     assert_close(db, dz.double().sum(0), rtol=2e-5, what="bias grad")
 
 
+# The epilogue has an interior path (16-byte aligned C, whole 32 x 16 chunks) and an edge path (last rows / columns,
+# unaligned C, Sigmoid): every activation through both, forward and dgrad, rows that end inside a chunk.
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+@pytest.mark.parametrize("n,k,o,ld_out", [(4099, 256, 256, 256), (4099, 256, 256, 257), (333, 71, 256, 256), (70000, 256, 80, 80),
+                                          (4099, 64, 40, 43)])
+def test_tc_epilogue_paths_vs_fp64(act, n, k, o, ld_out):
+    from multimodalstudio_b200 import ops
+    torch.manual_seed(act + n + o)
+    x = torch.randn(n, (k + 3) // 4 * 4, device=DEV)[:, :k] * 0.3
+    w = torch.randn(o, k, device=DEV) * 0.05
+    b = torch.randn(o, device=DEV) * 0.05
+    pw, pwt = ops.pack_weight(w, False, 3), ops.pack_weight(w, True, 3)
+    beta = 100.0
+    z = x.double() @ w.double().T + b.double()
+    ref = {0: z, 1: torch.relu(z), 2: torch.nn.functional.softplus(z, beta=beta, threshold=20.0), 3: torch.sigmoid(z)}[act]
+    y = torch.full((n, ld_out), float("nan"), device=DEV)[:, :o]
+    ops.linear_fwd_tc(x, pw, b, o, act, beta, 3, out=y)
+    assert_close(y, ref, rtol=2e-5, what="fwd")
+    # dgrad: dx = dz W * act'(y_prev), y_prev = a stored activation of width k
+    yp = {0: None, 1: torch.relu(x), 2: torch.nn.functional.softplus(x, beta=beta, threshold=20.0), 3: torch.sigmoid(x)}[act]
+    dz = torch.randn(n, o, device=DEV)
+    dx = torch.full((n, k + (ld_out - o)), float("nan"), device=DEV)[:, :k]
+    ops.linear_bwd_data_tc(dz, pwt, k, yp, act, beta, 3, out=dx)
+    der = {0: 1.0, 1: (x.double() > 0).double(), 2: torch.sigmoid(beta * x.double()), 3: None}[act]
+    if act == 3:
+        s = torch.sigmoid(x.double())
+        der = s * (1 - s)
+    assert_close(dx, (dz.double() @ w.double()) * der, rtol=2e-5, what="dgrad")
+
+
+@pytest.mark.parametrize("n,w,lds,ldd,off", [(0, 8, 8, 8, 0), (1000, 256, 256, 320, 32), (1000, 7, 9, 12, 1), (131, 4, 4, 8, 2)])
+def test_copy_rows_and_act_bwd(n, w, lds, ldd, off):
+    from multimodalstudio_b200 import ops
+    from multimodalstudio_b200._lib import call, ptr
+    import ctypes
+    torch.manual_seed(n + w)
+    src = torch.randn(n, lds, device=DEV)[:, :w]
+    dst = torch.zeros(n, ldd + off, device=DEV)
+    call("mmsb_copy_rows", ptr(src), ctypes.c_int64(lds), ptr(dst[:, off:]), ctypes.c_int64(ldd + off), ctypes.c_int64(n),
+         ctypes.c_int32(w), ops.stream_ptr())
+    assert torch.equal(dst[:, off:off + w], src) and float(dst[:, off + w:].abs().sum()) == 0 and float(dst[:, :off].abs().sum()) == 0
+    if n:
+        y = torch.rand(n, lds, device=DEV)[:, :w]
+        dy = torch.randn(n, ldd, device=DEV)[:, :w]
+        dz = torch.empty(n, lds, device=DEV)[:, :w]
+        for act, der in ((1, (y > 0).float()), (2, 1 - torch.exp(-100.0 * y.double())), (3, y * (1 - y))):
+            call("mmsb_act_bwd", ptr(dy), ctypes.c_int64(ldd), ptr(y), ctypes.c_int64(lds), ptr(dz), ctypes.c_int64(lds),
+                 ctypes.c_int64(n), ctypes.c_int32(w), ctypes.c_int32(act), ctypes.c_float(100.0), ops.stream_ptr())
+            assert_close(dz, dy.double() * der.double(), rtol=1e-5, what=f"act_bwd {act}")
+
+
 @pytest.mark.parametrize("prec", [0, 1, 3])
 def test_mlp_precision_modes_agree(prec):
     """The same MLP through the fp32 SIMT path, single-pass TF32 and 3xTF32."""
