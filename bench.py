@@ -289,6 +289,7 @@ def main():
         msk = {k: 0.0 for k in flops}
         cnt = {k: 0 for k in flops}
         hb = {"mmsb_hashgrid_fwd": [0.0, 0.0, 0], "mmsb_hashgrid_bwd": [0.0, 0.0, 0]}
+        shapes = {}     # (class, rows, in, out) -> [flops, ms, launches] over the two instrumented steps
         for name, ms, a in rec:
             if name in LAYER:
                 cls, j = LAYER[name]
@@ -296,6 +297,10 @@ def main():
                 flops[cls] += 2.0 * n * k * o
                 msk[cls] += ms
                 cnt[cls] += 1
+                sh = shapes.setdefault((cls, n, k, o), [0.0, 0.0, 0])
+                sh[0] += 2.0 * n * k * o
+                sh[1] += ms
+                sh[2] += 1
                 if name.endswith("_tc"):
                     tc_ms += ms
             elif name in hb:
@@ -323,6 +328,17 @@ def main():
                     # fp32-accurate products cost three TF32 MMAs each and TF32 runs at half the bf16 rate:
                     "ceiling_3xtf32": tf_sust / 6.0, "frac_of_3xtf32_ceiling": ach / (tf_sust / 6.0),
                     "per_class": {c: {"tflops": flops[c] / max(msk[c], 1e-9) / 1e9, "ms_per_step": msk[c] / 2, "launches": cnt[c] // 2} for c in flops}}
+            # the same figure for the single most expensive layer shape of every class (a 256 -> 256 layer of the SDF batch):
+            # what the kernel reaches where it is tensor-bound, measured live like the class averages
+            big = {}
+            for c in flops:
+                cand = [(v[1], key, v) for key, v in shapes.items() if key[0] == c]
+                if cand:
+                    _, key, v = max(cand)
+                    tf = v[0] / max(v[1], 1e-9) / 1e9
+                    big[c] = {"rows": key[1], "in": key[2], "out": key[3], "launches_per_step": v[2] // 2, "ms_per_launch": v[1] / v[2],
+                              "tflops": tf, "frac_of_bf16_peak": tf / tf_sust, "frac_of_3xtf32_ceiling": tf / (tf_sust / 6.0)}
+            roof["largest_shape"] = big
         hk = max(hb, key=lambda k: hb[k][1])
         if hb[hk][1] > 0:
             ach = hb[hk][0] / (hb[hk][1] / 1e3) / 1e9
