@@ -723,20 +723,46 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
 // Converter step of one landed A k-block (TMA path): this thread's four 16-byte chunks.  All shared-memory reads are
 // issued before the first dependent instruction (the accesses are volatile asm: the compiler keeps their order), so a
 // k-block costs one shared-memory latency instead of four.
+// generated operand of the products below a fused head: hd[row] * hw[col] * act'(y), 4 columns; the activation is
+// dispatched once per 16 bytes, not per element
+template <int ACT>
+__device__ __forceinline__ float4 gen_dz4(const float4& y, float d, const float4& hw4, float p) {
+  const float4 a = act_bwd4<ACT>(y, p);
+  return make_float4(d * hw4.x * a.x, d * hw4.y * a.y, d * hw4.z * a.z, d * hw4.w * a.w);
+}
+__device__ __forceinline__ float4 gen_dz4_rt(const float4& y, float d, const float4& hw4, int act, float p) {
+  switch (act) {
+    case MMSB_ACT_SOFTPLUS: return gen_dz4<MMSB_ACT_SOFTPLUS>(y, d, hw4, p);
+    case MMSB_ACT_RELU: return gen_dz4<MMSB_ACT_RELU>(y, d, hw4, p);
+    case MMSB_ACT_SIGMOID: return gen_dz4<MMSB_ACT_SIGMOID>(y, d, hw4, p);
+    default: return gen_dz4<MMSB_ACT_NONE>(y, d, hw4, p);
+  }
+}
+template <int ACT>
+__device__ __forceinline__ void generate_rows(float4 (&x)[4], uint32_t hi, const uint32_t (&off)[4], const float (&hd)[4],
+                                              const float4& hw4, float hact_param) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 d = act_bwd4<ACT>(x[i], hact_param);
+    x[i].x = hd[i] * hw4.x * d.x;
+    x[i].y = hd[i] * hw4.y * d.y;
+    x[i].z = hd[i] * hw4.z * d.z;
+    x[i].w = hd[i] * hw4.w * d.w;
+    sts128(hi + off[i], x[i]);
+  }
+}
 template <int NPARTS>
 __device__ __forceinline__ void convert_block(uint32_t hi, uint32_t lo, const uint32_t (&off)[4], bool gen, const float (&hd)[4],
                                               const float4& hw4, int hact, float hact_param) {
   float4 x[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) x[i] = lds128(hi + off[i]);
-  if (gen) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      x[i].x = hd[i] * hw4.x * act_bwd_from_y(x[i].x, hact, hact_param);
-      x[i].y = hd[i] * hw4.y * act_bwd_from_y(x[i].y, hact, hact_param);
-      x[i].z = hd[i] * hw4.z * act_bwd_from_y(x[i].z, hact, hact_param);
-      x[i].w = hd[i] * hw4.w * act_bwd_from_y(x[i].w, hact, hact_param);
-      sts128(hi + off[i], x[i]);
+  if (gen) {      // activation chosen once per k-block (warp-uniform), not per element
+    switch (hact) {
+      case MMSB_ACT_SOFTPLUS: generate_rows<MMSB_ACT_SOFTPLUS>(x, hi, off, hd, hw4, hact_param); break;
+      case MMSB_ACT_RELU: generate_rows<MMSB_ACT_RELU>(x, hi, off, hd, hw4, hact_param); break;
+      case MMSB_ACT_SIGMOID: generate_rows<MMSB_ACT_SIGMOID>(x, hi, off, hd, hw4, hact_param); break;
+      default: generate_rows<MMSB_ACT_NONE>(x, hi, off, hd, hw4, hact_param); break;
     }
   }
   if (NPARTS == 2) {
@@ -927,14 +953,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const __grid_consta
         hw4 = kb * TK + c * 4 < g.K ? load_cols4(g.hw, kb * TK + c * 4, g.K) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto generate = [&](float4 y, float d) {
-      float4 a;
-      a.x = d * hw4.x * act_bwd_from_y(y.x, g.hact, g.hact_param);
-      a.y = d * hw4.y * act_bwd_from_y(y.y, g.hact, g.hact_param);
-      a.z = d * hw4.z * act_bwd_from_y(y.z, g.hact, g.hact_param);
-      a.w = d * hw4.w * act_bwd_from_y(y.w, g.hact, g.hact_param);
-      return a;
-    };
+    auto generate = [&](float4 y, float d) { return gen_dz4_rt(y, d, hw4, g.hact, g.hact_param); };
     int64_t it = grp;
     if (it < iters) load_block(it);
     while (it < iters) {
@@ -1472,10 +1491,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
             const float4 y = va[i];
             const float d = hd[i];
             hsum.x = fmaf(d, y.x, hsum.x); hsum.y = fmaf(d, y.y, hsum.y); hsum.z = fmaf(d, y.z, hsum.z); hsum.w = fmaf(d, y.w, hsum.w);
-            va[i].x = d * hw4.x * act_bwd_from_y(y.x, g.hact, g.hact_param);
-            va[i].y = d * hw4.y * act_bwd_from_y(y.y, g.hact, g.hact_param);
-            va[i].z = d * hw4.z * act_bwd_from_y(y.z, g.hact, g.hact_param);
-            va[i].w = d * hw4.w * act_bwd_from_y(y.w, g.hact, g.hact_param);
+            va[i] = gen_dz4_rt(y, d, hw4, g.hact, g.hact_param);
           }
           split_store4<NPARTS>(a_hi, a_hi + PART, mn_offset(ca, ka + 8 * i), va[i]);
           colsum.x += va[i].x; colsum.y += va[i].y; colsum.z += va[i].z; colsum.w += va[i].w;
