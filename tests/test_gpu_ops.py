@@ -462,14 +462,18 @@ def test_tc_epilogue_paths_vs_fp64(act, n, k, o, ld_out):
     beta = 100.0
     z = x.double() @ w.double().T + b.double()
     ref = {0: z, 1: torch.relu(z), 2: torch.nn.functional.softplus(z, beta=beta, threshold=20.0), 3: torch.sigmoid(z)}[act]
-    y = torch.full((n, ld_out), float("nan"), device=DEV)[:, :o]
+    ybuf = torch.full((n + 64, ld_out), float("nan"), device=DEV)      # guard rows / pad columns must stay untouched
+    y = ybuf[:n, :o]
     ops.linear_fwd_tc(x, pw, b, o, act, beta, 3, out=y)
     assert_close(y, ref, rtol=2e-5, what="fwd")
+    assert bool(torch.isnan(ybuf[n:]).all()) and bool(torch.isnan(ybuf[:n, o:]).all()), "forward wrote outside C"
     # dgrad: dx = dz W * act'(y_prev), y_prev = a stored activation of width k
     yp = {0: None, 1: torch.relu(x), 2: torch.nn.functional.softplus(x, beta=beta, threshold=20.0), 3: torch.sigmoid(x)}[act]
     dz = torch.randn(n, o, device=DEV)
-    dx = torch.full((n, k + (ld_out - o)), float("nan"), device=DEV)[:, :k]
+    dxbuf = torch.full((n + 64, k + (ld_out - o)), float("nan"), device=DEV)
+    dx = dxbuf[:n, :k]
     ops.linear_bwd_data_tc(dz, pwt, k, yp, act, beta, 3, out=dx)
+    assert bool(torch.isnan(dxbuf[n:]).all()) and bool(torch.isnan(dxbuf[:n, k:]).all()), "dgrad wrote outside C"
     der = {0: 1.0, 1: (x.double() > 0).double(), 2: torch.sigmoid(beta * x.double()), 3: None}[act]
     if act == 3:
         s = torch.sigmoid(x.double())
