@@ -30,6 +30,9 @@ namespace tc {
 // The fragment-layout epilogue (tcgen05.ld.16x256b, no shared-memory transpose) measures the same as the transposed one;
 // compiling both into the kernels only costs instruction-cache footprint, so it is a build-time option
 // (make EXTRA=-DMMSB_TC_FRAG_EPILOGUE=1, then MMSB_TC_DIRECT=2 selects it).
+#ifndef MMSB_TC_PAIR_PROD_WARPS
+#define MMSB_TC_PAIR_PROD_WARPS 4
+#endif
 #ifndef MMSB_TC_EPI_WARPS
 #define MMSB_TC_EPI_WARPS 8
 #endif
@@ -48,6 +51,11 @@ constexpr int BPART = NT * 128;    // bytes reserved for one B part of a stage
 constexpr int EPI_WARPS = MMSB_TC_EPI_WARPS, PROD_WARPS = 8;   // epilogue warps: a multiple of 4 (TMEM lane quadrants); 2 producer groups
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int THREADS = (EPI_WARPS + PROD_WARPS + 2) * 32;   // rows kernel: + B-loader warp + MMA warp
+// pair kernels: 4 converter warps -> 14 warps per CTA: at most 4 warps per SM sub-partition, i.e. up to 128 registers per
+// thread (18 warps put 5 on one sub-partition: 96), which the dgrad epilogue needs to read TMEM ahead
+constexpr int PAIR_PROD_WARPS = MMSB_TC_PAIR_PROD_WARPS;
+constexpr int PAIR_PROD_THREADS = PAIR_PROD_WARPS * 32;
+constexpr int PAIR_THREADS = (EPI_WARPS + PAIR_PROD_WARPS + 2) * 32;
 constexpr int WG_STAGE_WARPS = 16;                           // weight-gradient kernel: 2 groups of 8 staging warps
 constexpr int WG_THREADS = (WG_STAGE_WARPS + 2) * 32;        // + MMA warp + TMA loader warp
 constexpr int CH = 16;                                       // accumulator columns per epilogue chunk
@@ -377,14 +385,15 @@ __device__ __forceinline__ void load_colvecs(const EpiArgs& e, ColVecs& cv, int 
   if (EPI == EPI_DGRAD && e.r1_d) cv.r4 = load_cols4_in(e.r1_w, col);
 }
 
-template <int EPI, int ACT, typename Next>
+template <int EPI, int ACT, bool RICH, typename Next>
 __device__ __forceinline__ void epilogue_rows_in(const EpiArgs& e, const float* stg, const YPrev& yp, const ColVecs& cv,
                                                  int lane, int64_t row0, int col0, float (&hacc)[4], Next issue_next) {
   const int q4 = lane & 3, r0 = lane >> 2;
   const int col = col0 + 4 * q4;
   const float4 b4 = cv.b4, h4 = cv.h4, r4 = cv.r4;
-  // rows in flight per lane (the dgrad kernels also hold two derivative operands: fewer registers left)
-  constexpr int G = EPI == EPI_DGRAD ? MMSB_TC_EPI_ILP / 2 : MMSB_TC_EPI_ILP;
+  // rows in flight per lane (the dgrad kernels also hold two derivative operands: fewer registers left, unless the
+  // kernel runs with the 128-register budget of the 14-warp pair CTAs, RICH)
+  constexpr int G = (EPI == EPI_DGRAD && !RICH) ? MMSB_TC_EPI_ILP / 2 : MMSB_TC_EPI_ILP;
   const uint32_t src = smem_u32(stg + r0 * STG_LD + 4 * q4);
   float* dst = e.C ? e.C + (row0 + r0) * e.ldc + col : nullptr;
   const int64_t step = 8 * e.ldc;
@@ -501,16 +510,16 @@ template <int EPI>
 __device__ __forceinline__ int chunk_act(const EpiArgs& e) {
   return EPI == EPI_FWD ? e.act : (EPI == EPI_DGRAD && e.yprev ? e.act_prev : MMSB_ACT_NONE);
 }
-template <int EPI, typename Next>
+template <int EPI, bool RICH, typename Next>
 __device__ __forceinline__ void epilogue_chunk_rows(const EpiArgs& e, float* stg, const YPrev& yp, const ColVecs& cv,
                                                     bool interior, int act, int lane, int64_t row0, int col0, bool vec_ok,
                                                     float (&hacc)[4], Next issue_next) {
   __syncwarp();
   if (interior) {
     switch (act) {
-      case MMSB_ACT_RELU: epilogue_rows_in<EPI, MMSB_ACT_RELU>(e, stg, yp, cv, lane, row0, col0, hacc, issue_next); break;
-      case MMSB_ACT_SOFTPLUS: epilogue_rows_in<EPI, MMSB_ACT_SOFTPLUS>(e, stg, yp, cv, lane, row0, col0, hacc, issue_next); break;
-      default: epilogue_rows_in<EPI, MMSB_ACT_NONE>(e, stg, yp, cv, lane, row0, col0, hacc, issue_next); break;
+      case MMSB_ACT_RELU: epilogue_rows_in<EPI, MMSB_ACT_RELU, RICH>(e, stg, yp, cv, lane, row0, col0, hacc, issue_next); break;
+      case MMSB_ACT_SOFTPLUS: epilogue_rows_in<EPI, MMSB_ACT_SOFTPLUS, RICH>(e, stg, yp, cv, lane, row0, col0, hacc, issue_next); break;
+      default: epilogue_rows_in<EPI, MMSB_ACT_NONE, RICH>(e, stg, yp, cv, lane, row0, col0, hacc, issue_next); break;
     }
   } else {
     issue_next();
@@ -615,7 +624,7 @@ __device__ __forceinline__ void epilogue_chunk_frag_dispatch(const EpiArgs& e, c
 
 // All chunks of one accumulator that belong to this warp (quadrant q = warp % 4, chunks c = warp / 4, + EPI_WARPS / 4, ...).
 // `release` is called by every lane right after the warp's last TMEM read (frees the accumulator for the MMA warp).
-template <int EPI, typename Release>
+template <int EPI, bool RICH, typename Release>
 __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_acc, int w, float* stg, int warp, int lane,
                                               int64_t row_base, int col_base, bool vec_ok, bool vec_y, YPrev& y_cur,
                                               Release release) {
@@ -695,7 +704,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
   // TMEM read of chunk c + STEP (and, dgrad, its derivative operand) is issued and stays in flight while chunk c is
   // processed from shared memory.  One call site, loop not unrolled: the code of the activation variants exists once.
   // (dgrad: the derivative operand of the next chunk is what is kept in flight, the registers do not allow both)
-  constexpr bool LD_AHEAD = EPI != EPI_DGRAD;
+  constexpr bool LD_AHEAD = EPI != EPI_DGRAD || RICH;
   uint32_t v[CH];
   if (LD_AHEAD) tmem_ld16(tmem_acc + uint32_t(first * CH) + (uint32_t(q * 32) << 16), v);
   const int act = chunk_act<EPI>(e);
@@ -705,14 +714,14 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
     if (!LD_AHEAD) tmem_ld16(tmem_acc + uint32_t(c * CH) + (uint32_t(q * 32) << 16), v);
     const bool interior = chunk_is_interior<EPI>(e, row0, col_base + c * CH, vec_ok, act);
     ColVecs cv;
-    if (interior && EPI != EPI_DGRAD) load_colvecs<EPI>(e, cv, lane, col_base + c * CH);
+    if (interior && (EPI != EPI_DGRAD || RICH)) load_colvecs<EPI>(e, cv, lane, col_base + c * CH);
     tmem_ld_wait();
     epilogue_stage(v, stg, lane);
     if (cn >= nch) release();
-    if (interior && EPI == EPI_DGRAD) load_colvecs<EPI>(e, cv, lane, col_base + c * CH);   // (no registers to spare earlier)
+    if (interior && EPI == EPI_DGRAD && !RICH) load_colvecs<EPI>(e, cv, lane, col_base + c * CH);   // (no registers to spare earlier)
     YPrev y_next;
     if (cn < nch) load_yprev<EPI>(e, y_next, lane, row0, col_base + cn * CH, vec_y);
-    epilogue_chunk_rows<EPI>(e, stg, y_cur, cv, interior, act, lane, row0, col_base + c * CH, vec_ok, hacc, [&]() {
+    epilogue_chunk_rows<EPI, RICH>(e, stg, y_cur, cv, interior, act, lane, row0, col_base + c * CH, vec_ok, hacc, [&]() {
       if (LD_AHEAD && cn < nch) tmem_ld16(tmem_acc + uint32_t(cn * CH) + (uint32_t(q * 32) << 16), v);
     });
     if (EPI == EPI_DGRAD && cn < nch) y_cur = y_next;
@@ -873,7 +882,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const __grid_consta
         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       };
       if (g.dbg & 2) release();   // dev: no epilogue work
-      else epilogue_tile<EPI>(g.epi, tmem + acc * NT, w, stg, warp, lane, mt * TM, nt * NT, vec_ok, vec_y, y_cur, release);
+      else epilogue_tile<EPI, false>(g.epi, tmem + acc * NT, w, stg, warp, lane, mt * TM, nt * NT, vec_ok, vec_y, y_cur, release);
     }
   } else if (warp < EPI_WARPS + PROD_WARPS) {
     if constexpr (TMA_A) {
@@ -1110,7 +1119,7 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, 
 }
 
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
     tc_rows_pair_kernel(const __grid_constant__ RowsArgs g, const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b) {
   constexpr int S = PAIR_STAGES;
   constexpr int STAGE = PAIR_STAGE;
@@ -1132,7 +1141,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
   const int64_t total_ptiles = m_ptiles * g.n_tiles;
   if (t == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(bar_full + 8 * s, 2 * PROD_WARPS + 1);   // both CTAs' converter warps + the leader loader's expect_tx
+      mbar_init(bar_full + 8 * s, 2 * PAIR_PROD_WARPS + 1);   // both CTAs' converter warps + the leader loader's expect_tx
       mbar_init(bar_empty + 8 * s, 1);
       mbar_init(bar_raw + 8 * s, 1);
     }
@@ -1184,45 +1193,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         if (lane == 0) mbar_arrive_leader(bar_tempty + 8 * acc);
       };
       if (g.dbg & 2) release();   // dev: no epilogue work
-      else epilogue_tile<EPI>(g.epi, tmem + acc * NT, NT, stg, warp, lane, m0, nt * NT, vec_ok, vec_y, y_cur, release);
+      else epilogue_tile<EPI, (PAIR_THREADS <= 512)>(g.epi, tmem + acc * NT, NT, stg, warp, lane, m0, nt * NT, vec_ok, vec_y, y_cur, release);
     }
-  } else if (warp < EPI_WARPS + PROD_WARPS) {
+  } else if (warp < EPI_WARPS + PAIR_PROD_WARPS) {
     // ================= converters (this CTA's 128 rows of A) =================
     const int p = t - EPI_WARPS * 32;
     const int64_t iters = my_ptiles * g.nkb;
     const int c = p & 7, r_base = p >> 3;
+    constexpr int NCH = PART / (PAIR_PROD_THREADS * 16);      // 16-byte chunks per converter thread and k-block (4 or 8)
+    constexpr int RSTEP = PAIR_PROD_THREADS / 8;              // generated operand: rows r_base + RSTEP i
+    static_assert(NCH % 4 == 0, "whole groups of four chunks");
     for (int64_t it = 0; it < iters; ++it) {
       const uint32_t s = uint32_t(it % S);
-      float hd[4];
+      float hd[NCH];
       float4 hw4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (g.hd) {
         const int64_t tl = it / g.nkb;
         const int kb = int(it - tl * g.nkb);
         const int64_t m0 = ((pair + tl * npairs) / g.n_tiles) * 2 * TM + rank * TM;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int64_t row = m0 + r_base + 32 * i;
+        for (int i = 0; i < NCH; ++i) {
+          const int64_t row = m0 + r_base + RSTEP * i;
           hd[i] = row < g.M ? __ldg(g.hd + row) : 0.f;
         }
         if (kb * TK + c * 4 < g.K) hw4 = load_cols4(g.hw, kb * TK + c * 4, g.K);
       }
       mbar_wait(bar_raw + 8 * s, uint32_t(it / S) & 1);
       const uint32_t hi = smem_u32(smem + s * STAGE), lo = hi + PART;
-      uint32_t off[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        off[i] = uint32_t(p + i * PROD_THREADS) * 16u;
-        if (g.hd) {
-          const int r = r_base + 32 * i;
-          off[i] = uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4);
+      for (int h = 0; h < NCH / 4; ++h) {
+        uint32_t off[4];
+        float hd4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ii = 4 * h + i;
+          off[i] = uint32_t(p + ii * PAIR_PROD_THREADS) * 16u;
+          if (g.hd) {
+            const int r = r_base + RSTEP * ii;
+            off[i] = uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4);
+          }
+          hd4[i] = g.hd ? hd[ii] : 0.f;
         }
+        convert_block<2>(hi, lo, off, g.hd != nullptr, hd4, hw4, g.hact, g.hact_param);
       }
-      convert_block<2>(hi, lo, off, g.hd != nullptr, hd, hw4, g.hact, g.hact_param);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(bar_full + 8 * s);
     }
-  } else if (warp == EPI_WARPS + PROD_WARPS) {
+  } else if (warp == EPI_WARPS + PAIR_PROD_WARPS) {
     // ================= loader: this CTA's A k-block and its half of the weight k-block =================
     if (lane == 0) {
       const bool pf = g.prefetch != 0;
@@ -1248,7 +1266,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         }
       }
     }
-  } else if (warp == EPI_WARPS + PROD_WARPS + 1 && rank == 0) {
+  } else if (warp == EPI_WARPS + PAIR_PROD_WARPS + 1 && rank == 0) {
     // ================= MMA issuer (leader CTA) =================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(NT >> 3) << 17) | (uint32_t((2 * TM) >> 4) << 24);
@@ -1428,7 +1446,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
         mbar_wait(bar_tfull, 0);
         tc_fence_after();
         YPrev y_none;
-        epilogue_tile<EPI_ATOMIC>(e, tmem, w, stg, warp, lane, m0, n0, false, false, y_none, []() {});
+        epilogue_tile<EPI_ATOMIC, false>(e, tmem, w, stg, warp, lane, m0, n0, false, false, y_none, []() {});
       }
     } else if (TMA && warp == WG_STAGE_WARPS + 1) {
       // ================= loader: one tensor-map copy per 32-wide panel =================
@@ -1543,7 +1561,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
         mbar_wait(bar_tfull, 0);
         tc_fence_after();
         YPrev y_none;
-        epilogue_tile<EPI_ATOMIC>(e, tmem, w, stg, warp, lane, m0, n0, false, false, y_none, []() {});
+        epilogue_tile<EPI_ATOMIC, false>(e, tmem, w, stg, warp, lane, m0, n0, false, false, y_none, []() {});
       }
     } else if (warp == WG_STAGE_WARPS && (!PAIR || mt == 0)) {
       // ================= MMA issuer (pair: the leader CTA) =================
@@ -1718,7 +1736,7 @@ static int launch_rows_pair(const RowsArgs& g, const CUtensorMap& map_a, cudaStr
   const int64_t pairs = ptiles < kNumSMs / 2 ? ptiles : kNumSMs / 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * pairs));
-  cfg.blockDim = dim3(THREADS);
+  cfg.blockDim = dim3(PAIR_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g, map_a, map_b);
