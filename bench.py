@@ -314,7 +314,7 @@ def main():
             from multimodalstudio_b200 import ops as _ops
             path = {0: "fp32 SIMT GEMM", 1: "tcgen05 TF32", 3: "tcgen05 3xTF32 (3 MMAs per product, fp32-accurate)"}[_ops.MLP_PRECISION]
             traffic, traffic_note = None, None
-            tp = os.path.join(ROOT, "profiles", "r1e_traffic.json")
+            tp = os.path.join(ROOT, "profiles", "r1f_traffic.json")
             if os.path.exists(tp):
                 tj = json.load(open(tp))
                 if top in tj:
