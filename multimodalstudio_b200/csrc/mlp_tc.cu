@@ -6,19 +6,25 @@
 // accumulation in TMEM), which keeps the 1e-5 parity band of the fp32 reference on the tensor pipe.
 // Precision 1: single-pass TF32 (the reference's GPU runs use fp16 autocast; 1e-2 band).
 //
-// Two persistent, warp-specialised kernels, one CTA per SM:
-//   tc_rows_kernel  (forward, dgrad)   D[rows x N] = A[rows x K] * Bp[N x K]^T
-//       A  = activations, fp32 in global memory; 8 producer warps load them with a register prefetch, split
-//            them into hi/lo and store them into K-major SWIZZLE_128B shared-memory tiles;
-//       Bp = weights pre-split and pre-swizzled by pack_weight_kernel (once per step and layer), so one
-//            bulk async copy (TMA, cp.async.bulk + mbarrier complete_tx) lands a k-block of B in its stage;
-//       1 thread issues tcgen05.mma into one of two 128x256 fp32 accumulators in TMEM (512 columns), so the
-//       4 epilogue warps (tcgen05.ld -> bias/activation or activation derivative -> shared-memory transpose
-//       -> coalesced 128-byte stores) drain tile i while the MMAs of tile i+1 run.
+// Three persistent, warp-specialised kernels (one CTA per SM, or one CTA pair per two SMs):
+//   tc_rows_kernel  (forward, dgrad)   D[rows x N] = A[rows x K] * Bp[N x K]^T, 18 warps
+//       A  = activations, fp32 in global memory.  TMA path (16-byte aligned rows): a tensor-map copy lands the raw
+//            fp32 k-block as the hi tile (the tensor core reads fp32 as TF32 by truncation), 8 converter warps derive
+//            lo = rna(x - trunc(x)) from shared memory.  Otherwise 8 producer warps load with a register prefetch,
+//            split into hi / lo and store K-major SWIZZLE_128B tiles.
+//       Bp = weights pre-split and pre-swizzled by pack_weight_kernel (once per step and layer): one bulk async copy
+//            (cp.async.bulk + mbarrier complete_tx) lands a k-block of B in its stage;
+//       1 thread issues tcgen05.mma into one of two 128x256 fp32 accumulators in TMEM (512 columns), so the 8 epilogue
+//       warps (tcgen05.ld -> shared-memory transpose -> bias / activation or activation derivative -> 16-byte row
+//       stores; branch-free interior path, bounds-checked edge path) drain tile i while the MMAs of tile i+1 run.
+//   tc_rows_pair_kernel  the same products for 256-wide accumulators on CTA pairs (tcgen05.mma.cta_group::2, M = 256
+//       across two SMs): each CTA stages its 128 rows of A and HALF of the weight k-block, 3-stage ring of 64 KB,
+//       14 warps per CTA (8 epilogue, 4 converter, loader, MMA issuer) = up to 128 registers per thread.
 //   tc_wgrad_kernel (weight gradient)  dW[out x in] += dz[rows x out]^T * x[rows x in], split over rows
 //       both operands are MN-major in global memory and are staged without a transpose into MN-major
-//       SWIZZLE_128B_BASE32B tiles; the bias gradient (column sums of dz) is accumulated by the producers on the way;
-//       partial tiles are combined with coalesced fp32 reductions (red.global.add).
+//       SWIZZLE_128B_BASE32B tiles by 16 staging warps; the bias gradient (column sums of dz) is accumulated on the way;
+//       partial tiles are combined with coalesced fp32 reductions (red.global.add); PAIR variant: the two 128-row
+//       m-tiles of a 256 x 256 gradient on a CTA pair, each CTA staging half of the x columns.
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
