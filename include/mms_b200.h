@@ -367,8 +367,9 @@ int mmsb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
                     const float* grad_scale, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int32_t step, int64_t n, mmsb_stream_t stream);
 /* The same update, replayable from a CUDA graph: the step-dependent scalars live in device memory,
- * hyper = {lr, 1 - beta1^t, sqrt(1 - beta2^t)}; grad_sumsq (or NULL) + max_norm give the clip coefficient
- * min(1, max_norm / (sqrt(sumsq) + 1e-6)) of clip_grad_norm_ (pipelines/base_pipeline.py:232-248). */
+ * hyper = {lr, 1 - beta1^t, sqrt(1 - beta2^t), prescale}; the gradient is read as grad * prescale (1 / world size
+ * after a summing all-reduce = DDP's mean, 1 otherwise); grad_sumsq (or NULL) + max_norm give the clip coefficient
+ * min(1, max_norm / (sqrt(sumsq) * prescale + 1e-6)) of clip_grad_norm_ (pipelines/base_pipeline.py:232-248). */
 int mmsb_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                         const float* grad_sumsq, float max_norm, const float* hyper, float beta1, float beta2,
                         float eps, float weight_decay, int64_t n, mmsb_stream_t stream);

@@ -171,17 +171,19 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 
-// Same update with the per-step scalars in device memory (hyper = {lr, 1 - beta1^t, sqrt(1 - beta2^t)}) and the
-// clip coefficient min(1, max_norm / (sqrt(sumsq) + 1e-6)) evaluated in the kernel: nothing step-dependent is a
-// launch argument, so the launch can be replayed from a CUDA graph.
+// Same update with the per-step scalars in device memory (hyper = {lr, 1 - beta1^t, sqrt(1 - beta2^t), prescale}) and
+// the clip coefficient min(1, max_norm / (sqrt(sumsq) * prescale + 1e-6)) evaluated in the kernel: nothing step-dependent
+// is a launch argument, so the launch can be replayed from a CUDA graph.  prescale (1 / world size for DDP's gradient
+// mean, 1 otherwise) is folded in here instead of a separate pass over the all-reduced gradient: g := g * prescale
+// before the clip, i.e. the norm that is clipped is the norm of the averaged gradient.
 __global__ void __launch_bounds__(256) adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v,
                                                         const float* __restrict__ grad_sumsq, float max_norm,
                                                         const float* __restrict__ hyper, float beta1, float beta2,
                                                         float eps, float wd, int64_t n) {
-  const float lr = __ldg(hyper), bc1 = __ldg(hyper + 1), bc2_sqrt = __ldg(hyper + 2);
-  float gs = 1.f;
-  if (grad_sumsq) gs = fminf(__fdiv_rn(max_norm, __fadd_rn(__fsqrt_rn(__ldg(grad_sumsq)), 1e-6f)), 1.f);
+  const float lr = __ldg(hyper), bc1 = __ldg(hyper + 1), bc2_sqrt = __ldg(hyper + 2), pre = __ldg(hyper + 3);
+  float gs = pre;
+  if (grad_sumsq) gs = pre * fminf(__fdiv_rn(max_norm, __fadd_rn(__fmul_rn(__fsqrt_rn(__ldg(grad_sumsq)), pre), 1e-6f)), 1.f);
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     const float gr = g[i] * gs;
     float pv = p[i];

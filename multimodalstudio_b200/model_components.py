@@ -828,7 +828,12 @@ class LossManager:
         out += [getattr(self, name)._weight(step) for name in self.config.geometry_losses]
         return out
 
-    def compute_loss(self, outputs, targets, pixel_coords, step, eval_step=False, mosaick_patterns=None):
+    def compute_loss(self, outputs, targets, pixel_coords, step, eval_step=False, mosaick_patterns=None,
+                     loss_scales=None, geometry_count=None):
+        """`loss_scales` ({mod: n_batch / n_global}) and `geometry_count` (device fp32 [1], the global number of
+        in-sphere samples): set when the batch is one shard of a step's global batch (pipelines.ShardPlan) — every term
+        of the total is then `local sum / global count`, so shards add up to the reference's full-batch loss.  The
+        entries of `losses` stay the batch's own means."""
         losses = {}
         total_loss = 0.0
         for mod in self.modalities:
@@ -840,6 +845,8 @@ class LossManager:
             losses[mod] = loss
             if weight != 1:
                 losses[mod + "_weight"] = weight
+            if loss_scales is not None:
+                weight = weight * loss_scales[mod]
             total_loss = total_loss + weight * loss
         if not eval_step and self.config.geometry_losses:
             grads = [outputs[mod]["gradients"] for mod in self.modalities]
@@ -848,7 +855,7 @@ class LossManager:
             g = torch.cat(grads, dim=0)
             h = torch.cat(hess, dim=0) if all(x is not None for x in hess) else None
             m = torch.cat(masks, dim=0) if all(x is not None for x in masks) else None
-            eik, curv = ops.GeometryLossFn.apply(g, h, m)
+            eik, curv = ops.GeometryLossFn.apply(g, h, m, geometry_count)
             for loss_name in self.config.geometry_losses:
                 loss_fn = getattr(self, loss_name)
                 if loss_name == "eikonal_loss":

@@ -1056,15 +1056,20 @@ def mosaick_bands(coords, pattern, ph, pw, rendered):
 
 
 class GeometryLossFn(torch.autograd.Function):
-    """(eikonal, curvature) means over the unmasked samples of gradients/hessians [n,s,3]."""
+    """(eikonal, curvature) means over the unmasked samples of gradients/hessians [n,s,3].  `count` (device fp32 [1],
+    optional): divide the sums by this number instead of the batch's own unmasked-sample count — the GLOBAL count when
+    the batch is one shard of a step (pipelines.ShardPlan), so that the shards' losses and gradients add up to the
+    unsharded ones."""
 
     @staticmethod
-    def forward(ctx, gradients, hessians, ray_mask):
+    def forward(ctx, gradients, hessians, ray_mask, count=None):
         nr, s = gradients.shape[0], gradients.shape[1]
         g = _f(gradients).reshape(nr * s, 3)
         h = _f(hessians).reshape(nr * s, 3) if hessians is not None else None
         sums = torch.zeros((3,), device=g.device)
         call("mmsb_geometry_loss_fwd", ptr(g), ptr(h), ptr(ray_mask), _i32(s), ptr(sums), _i64(nr * s), stream_ptr())
+        if count is not None:
+            sums = torch.cat([sums[:2], _f(count.detach()).reshape(1)])
         ctx.save_for_backward(g, h, ray_mask, sums)
         ctx.cfg = (s, gradients.shape)
         cnt = sums[2].clamp_min(1.0)
@@ -1080,7 +1085,7 @@ class GeometryLossFn(torch.autograd.Function):
         dc = _f(d_curv).reshape(1) if d_curv is not None else None
         call("mmsb_geometry_loss_bwd", ptr(g), ptr(h), ptr(ray_mask), _i32(s), ptr(sums), ptr(de), ptr(dc), ptr(dg),
              ptr(dh), _i64(g.shape[0]), stream_ptr())
-        return dg.reshape(shape), (dh.reshape(shape) if dh is not None else None), None
+        return dg.reshape(shape), (dh.reshape(shape) if dh is not None else None), None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -1096,7 +1101,7 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, grad_scale, lr, beta1, beta2, e
 
 
 def adamw_step_dev(param, grad, exp_avg, exp_avg_sq, grad_sumsq, max_norm, hyper, beta1, beta2, eps, weight_decay):
-    """hyper: device tensor [3] = {lr, 1 - beta1^t, sqrt(1 - beta2^t)} (graph-replayable AdamW)."""
+    """hyper: device tensor [4] = {lr, 1 - beta1^t, sqrt(1 - beta2^t), gradient prescale} (graph-replayable AdamW)."""
     call("mmsb_adamw_step_dev", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(grad_sumsq), _f32(max_norm or 0.0),
          ptr(hyper), _f32(beta1), _f32(beta2), _f32(eps), _f32(weight_decay), _i64(param.numel()), stream_ptr())
 

@@ -104,6 +104,63 @@ class DevicePixelSampler:
         return coords, targets
 
 
+class ShardPlan:
+    """How the global ray batch of ONE optimizer step is split ("strong" mode): rank r of G takes the
+    contiguous slice [r*R_m/G, (r+1)*R_m/G) of every modality m, so the modality mix of every rank is the global one;
+    a rank's slice is cut the same way into k micro-batches of at most `max_rays_per_micro` rays (all modalities
+    together) that run one after the other and accumulate their gradients.  Every loss is normalised by the GLOBAL count
+    (`loss_scales`: a micro-batch's mean times n_micro / n_global), so the sum of all shards' gradients — over
+    micro-batches in the flat buffer, over ranks by the summing all-reduce — IS the single-batch gradient.
+    Pure Python (no device work): tests/test_dist_cpu.py drives it under gloo."""
+
+    def __init__(self, global_counts: Dict[str, int], world_size: int = 1, rank: int = 0,
+                 max_rays_per_micro: Optional[int] = None):
+        if not (0 <= rank < world_size):
+            raise ValueError(f"rank {rank} outside world size {world_size}")
+        self.global_counts, self.world_size, self.rank = dict(global_counts), world_size, rank
+        self.local = {m: (rank * n // world_size, (rank + 1) * n // world_size) for m, n in global_counts.items()}
+        local_total = sum(b - a for a, b in self.local.values())
+        k = 1
+        if max_rays_per_micro is not None and local_total > max_rays_per_micro:
+            k = -(-local_total // max_rays_per_micro)
+            # per-modality rounding: a micro-batch holds at most sum_m ceil(L_m / k) rays
+            while sum(-(-(b - a) // k) for a, b in self.local.values()) > max_rays_per_micro:
+                k += 1
+        self.micro = []
+        for j in range(k):
+            self.micro.append({m: (a + j * (b - a) // k, a + (j + 1) * (b - a) // k) for m, (a, b) in self.local.items()})
+
+    def __len__(self):
+        return len(self.micro)
+
+    def loss_scales(self, j: int) -> Dict[str, float]:
+        """n_micro / n_global per modality: what a micro-batch's mean loss is multiplied with."""
+        return {m: (b - a) / max(self.global_counts[m], 1) for m, (a, b) in self.micro[j].items()}
+
+    def slice(self, j: int, tensors: Dict[str, torch.Tensor], base: str = "global") -> Dict[str, torch.Tensor]:
+        """Rows of micro-batch j out of per-modality tensors indexed globally (`base="global"`) or relative to this
+        rank's local slice (`base="local"`)."""
+        out = {}
+        for m, (a, b) in self.micro[j].items():
+            off = self.local[m][0] if base == "local" else 0
+            out[m] = tensors[m][a - off:b - off]
+        return out
+
+    def local_slice(self, tensors: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        return {m: tensors[m][a:b] for m, (a, b) in self.local.items()}
+
+
+def all_reduce_flat(flat: torch.Tensor, group=None):
+    """The ONE data-path collective of the hot path: summing all-reduce of a flat fp32 gradient buffer
+    over NCCL (gloo in the CPU tests).  The division by the world size of DDP's mean is not applied here: the optimizer
+    kernel folds it into its gradient read (`FlatAdamW.prescale`)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return flat
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
 class FlatAdamW:
     """One AdamW "optimizer" of the reference (engine/optimizers.py, method_configs.py:260-269) over a flat
     fp32 buffer: parameters and gradients are views into two contiguous tensors, so zero-grad is one memset,
@@ -132,9 +189,16 @@ class FlatAdamW:
         self.step_count = 0
         self.sumsq = torch.zeros(1, device=dev)
         self.scale = torch.ones(1, device=dev)
-        # per-step scalars of the graph-replayable update: {lr, 1 - beta1^t, sqrt(1 - beta2^t)}
-        self.hyper = torch.zeros(3, device=dev)
-        self.hyper_host = torch.zeros(3).pin_memory() if dev.type == "cuda" else torch.zeros(3)
+        # per-step scalars of the graph-replayable update: {lr, 1 - beta1^t, sqrt(1 - beta2^t), gradient prescale}.
+        # They are staged through a RING of pinned slots, one per step, each guarded by the event of its last upload:
+        # the CPU runs ahead of the GPU, and a single pinned buffer would be overwritten for step t+k before the
+        # asynchronous copy of step t has read it.
+        self.prescale = 1.0          # 1 / world size when the all-reduce sums per-rank MEAN losses (DDP semantics)
+        self.hyper = torch.zeros(4, device=dev)
+        self.HYPER_SLOTS = 64
+        on_gpu = dev.type == "cuda"
+        self.hyper_ring = torch.zeros(self.HYPER_SLOTS, 4).pin_memory() if on_gpu else torch.zeros(self.HYPER_SLOTS, 4)
+        self.hyper_events = [None] * self.HYPER_SLOTS
 
     def zero_grad(self):
         self.grad.zero_()
@@ -147,10 +211,12 @@ class FlatAdamW:
         for p in self.params:
             p.grad = None
 
-    def gather_grads(self):
+    def gather_grads(self, accumulate: bool = False):
         """After backward: one memset + one multi-tensor copy bring the gradients into the flat buffer (the layout the
-        clip, AdamW and the NCCL all-reduce work on)."""
-        self.grad.zero_()
+        clip, AdamW and the NCCL all-reduce work on).  `accumulate`: add to what the flat buffer holds instead (gradient
+        accumulation over the micro-batches of one step; the caller zeroes the buffer before the first one)."""
+        if not accumulate:
+            self.grad.zero_()
         src, dst = [], []
         for p, g in zip(self.params, self.grad_views):
             if p.grad is not None:
@@ -158,16 +224,25 @@ class FlatAdamW:
                 dst.append(g)
             p.grad = g
         if src:
-            torch._foreach_copy_(dst, src)
+            if accumulate:
+                torch._foreach_add_(dst, src)
+            else:
+                torch._foreach_copy_(dst, src)
 
     def step(self, lr_factor: float = 1.0):
         self.step_count += 1
+        ops.clear_pack_cache()       # the packed layer operands are functions of the parameters this call rewrites
         scale = None
         if self.max_norm is not None:
             # clip_grad_norm_(max_norm, error_if_nonfinite=False): coef = max_norm / (norm + 1e-6), clamped to 1
             self.sumsq.zero_()
             ops.sumsq(self.grad, self.sumsq)
-            torch.clamp(self.max_norm / (self.sumsq.sqrt() + 1e-6), max=1.0, out=self.scale)
+            torch.clamp(self.max_norm / (self.sumsq.sqrt() * self.prescale + 1e-6), max=1.0, out=self.scale)
+            if self.prescale != 1.0:
+                self.scale.mul_(self.prescale)
+            scale = self.scale
+        elif self.prescale != 1.0:
+            self.scale.fill_(self.prescale)
             scale = self.scale
         ops.adamw_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, scale, self.lr * lr_factor, self.betas[0],
                        self.betas[1], self.eps, self.wd, self.step_count)
@@ -176,13 +251,24 @@ class FlatAdamW:
     def advance(self, lr_factor: float = 1.0):
         """Host side of `step_dev`: bumps the step count and uploads this step's scalars (outside any graph)."""
         self.step_count += 1
-        self.hyper_host[0] = self.lr * lr_factor
-        self.hyper_host[1] = 1.0 - self.betas[0] ** self.step_count
-        self.hyper_host[2] = math.sqrt(1.0 - self.betas[1] ** self.step_count)
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        slot = self.step_count % self.HYPER_SLOTS
+        ev = self.hyper_events[slot]
+        if ev is not None:
+            ev.synchronize()         # only ever waits when the CPU is HYPER_SLOTS steps ahead of the GPU
+        host = self.hyper_ring[slot]
+        host[0] = self.lr * lr_factor
+        host[1] = 1.0 - self.betas[0] ** self.step_count
+        host[2] = math.sqrt(1.0 - self.betas[1] ** self.step_count)
+        host[3] = self.prescale
+        self.hyper.copy_(host, non_blocking=True)
+        if self.hyper.is_cuda:
+            ev = self.hyper_events[slot] or torch.cuda.Event()
+            ev.record()
+            self.hyper_events[slot] = ev
 
     def step_dev(self):
         """Clip + AdamW with every step-dependent scalar read from device memory (CUDA-graph replayable)."""
+        ops.clear_pack_cache()       # the packed layer operands are functions of the parameters this call rewrites
         if self.max_norm is not None:
             self.sumsq.zero_()
             ops.sumsq(self.grad, self.sumsq)
@@ -229,38 +315,53 @@ class RawPipeline:
         self.callbacks = self.model.get_training_callbacks(TrainingCallbackAttributes(model=self.model, trainer=t))
         self.process_group = process_group
         self.model.train()
-        self._graph = None          # (key, static coords, static targets, fwd+bwd graph, optimizer graph, losses, total)
+        self._graphs = {}           # schedule key -> (static coords, static targets, static count, fwd+bwd graph, losses, total)
+        self._g_opt = None          # clip + AdamW graph (no step-dependent launch argument: one capture serves every step)
+        self._pool = None           # memory pool shared by the pipeline's graphs
         self._last_key = None
-        self.graph_launches = 0     # kernels of libmms_b200.so captured in one step's graphs
+        self.graph_launches = 0     # kernels of libmms_b200.so captured in one (micro-)batch's forward + backward graph
+        self.inputs_event = torch.cuda.Event() if self.device.type == "cuda" else None
 
     def run_callbacks(self, step):
         for cb in self.callbacks:
             cb.run_callback_at_location(step, TrainingCallbackLocation.BEFORE_TRAIN_ITERATION)
 
-    def forward_backward(self, coords, targets, step):
+    def forward_backward(self, coords, targets, step, loss_scales=None, geometry_count=None, accumulate=False):
+        """One forward + loss + backward over a (micro-)batch; gradients land in the optimizers' flat buffers
+        (`accumulate`: added to what they hold).  `loss_scales` / `geometry_count`: normalisation by the GLOBAL counts
+        when the batch is one shard of a step (see ShardPlan; LossManager.compute_loss)."""
         ops.clear_pack_cache()
         with torch.nn.utils.parametrize.cached():     # one weight-norm evaluation (and one operand pack) per step
             ray_bundles = self.ray_generator(coords)
             outputs = self.model(ray_bundles)
-        losses, total = self.loss_manager.compute_loss(outputs, targets, coords, step, mosaick_patterns=self.patterns)
+        losses, total = self.loss_manager.compute_loss(outputs, targets, coords, step, mosaick_patterns=self.patterns,
+                                                       loss_scales=loss_scales, geometry_count=geometry_count)
         for opt in self.optimizers.values():
             opt.detach_grads()
         total.backward()
         for opt in self.optimizers.values():
-            opt.gather_grads()
+            opt.gather_grads(accumulate)
         # detached: a caller holding on to the losses must not keep the autograd graph (and its AccumulateGrad
         # nodes, which remember the stream they were created on) alive into the next step / a graph capture
         return {k: (v.detach() if torch.is_tensor(v) else v) for k, v in losses.items()}, total.detach()
 
-    def all_reduce_gradients(self):
-        """DDP semantics of the reference (mean over ranks) — one flat NCCL all-reduce per optimizer."""
+    def _world(self):
         import torch.distributed as dist
-        if self.process_group is None and not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-            return
-        ws = dist.get_world_size(self.process_group)
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.process_group)
+        return 1
+
+    def all_reduce_gradients(self, mean: bool = True):
+        """The gradient exchange of the reference's DDP: ONE summing NCCL all-reduce per optimizer over
+        its flat gradient buffer.  `mean=True` (weak scaling, every rank a full batch with its own mean losses): the
+        1 / world size of DDP's average is folded into the optimizer kernel's gradient read (FlatAdamW.prescale), no
+        extra pass over the 138 MB.  `mean=False` (strong scaling, losses already normalised by the global counts): the
+        sum is the single-batch gradient."""
+        ws = self._world()
         for opt in self.optimizers.values():
-            dist.all_reduce(opt.grad, op=dist.ReduceOp.SUM, group=self.process_group)
-            opt.grad.mul_(1.0 / ws)
+            opt.prescale = 1.0 / ws if (mean and ws > 1) else 1.0
+            if ws > 1:
+                all_reduce_flat(opt.grad, self.process_group)
 
     def optimizer_step(self, step):
         f = multistep_warmup_factor(step, self.max_num_iterations)
@@ -275,12 +376,60 @@ class RawPipeline:
         self.optimizer_step(step)
         return losses, total
 
+    @torch.no_grad()
+    def count_unmasked_samples(self, coords) -> torch.Tensor:
+        """Device fp32 [1]: samples per ray x the number of rays of `coords` (all modalities) that hit the sphere — the
+        denominator of the geometry losses (losses.py:113-150 average over the compacted in-sphere samples).  Ray
+        generation + collider only: a few small launches."""
+        bundles = self.ray_generator(coords)
+        total = torch.zeros((), device=self.device)
+        for rb in bundles.values():
+            if rb is not None:
+                total = total + ops.sphere_collide(rb.origins, rb.directions, self.model.collider.collider.radius)[2].sum(dtype=torch.float32)
+        s = self.model.ray_sampler.config.num_samples + self.model.ray_sampler.config.num_samples_importance
+        return (total * float(s)).reshape(1)
+
+    def train_step_sharded(self, step, coords, targets, plan: ShardPlan, graphed: bool = True):
+        """One optimizer step over this rank's slice of a global batch (SURVEY §8(e) "strong" mode): `coords` / `targets`
+        hold the rank's LOCAL rows of every modality (device or pinned host memory), `plan` cuts them into micro-batches
+        whose gradients accumulate in the flat buffers; every loss is normalised by the global counts (rays per
+        modality: static; in-sphere samples: counted on the device and summed over the ranks), so the summing all-reduce
+        yields exactly the gradient of the unsharded batch.  Returns (losses of the last micro-batch, this rank's share
+        of the total loss)."""
+        self.run_callbacks(step)
+        dc = {m: c.to(self.device, non_blocking=True) for m, c in coords.items()}
+        dt = {m: t.to(self.device, non_blocking=True) for m, t in targets.items()}
+        self.inputs_event.record()       # the caller may reuse its pinned buffers once this event has completed
+        count = self.count_unmasked_samples(dc)
+        all_reduce_flat(count, self.process_group)
+        for opt in self.optimizers.values():
+            opt.grad.zero_()
+        total_sum, losses = torch.zeros((), device=self.device), None
+        for j in range(len(plan)):
+            cs, ts = plan.slice(j, dc, "local"), plan.slice(j, dt, "local")
+            scales = plan.loss_scales(j)
+            if graphed:
+                losses, total = self._fb_graphed(step, cs, ts, scales, count)
+            else:
+                losses, total = self.forward_backward(cs, ts, step, scales, count, accumulate=True)
+            total_sum = total_sum + total
+        self.all_reduce_gradients(mean=False)
+        if graphed:
+            self._optimizer_graphed(step)
+        else:
+            self.optimizer_step(step)
+        return losses, total_sum
+
     # ---- full-frame inference (SURVEY 8(f) row 3: utils/eval_utils.py:31-75, engine/evaluator.py:619-746) ----------
     @torch.no_grad()
-    def render(self, coords, chunk_rays: int = 32768):
+    def render(self, coords, chunk_rays: Optional[int] = None):
         """Renders pixel coordinates {mod: int32 [R,3]} in eval mode (deterministic sampling, no Hessian) in chunks of
-        `chunk_rays` rays per modality, all modalities of a chunk as one batch; returns {mod: [R, C]} (the modality's
-        own head; mosaicked pipelines select the pattern's channel per pixel like evaluator.py:721-746)."""
+        `chunk_rays` rays per modality (default: 4 Mi samples per chunk over all modalities), all modalities of a chunk
+        as one batch; returns {mod: [R, C]} (the modality's own head; mosaicked pipelines select the pattern's channel
+        per pixel like evaluator.py:721-746)."""
+        if chunk_rays is None:
+            cfg = self.model.ray_sampler.config
+            chunk_rays = max(256, (1 << 22) // ((cfg.num_samples + cfg.num_samples_importance) * max(len(coords), 1)))
         was_training = self.model.training
         self.model.eval()
         ops.clear_pack_cache()
@@ -329,69 +478,107 @@ class RawPipeline:
         return out.reshape(resolution, resolution, resolution)
 
     # ---- the same step replayed from CUDA graphs ------------------------------------------------------------
-    def _schedule_key(self, step, coords, targets):
+    def _schedule_key(self, step, coords, targets, scales=None):
         """Everything a captured step bakes into its launch arguments: the schedule state the callbacks set
-        (level mask, delta, anneal), the loss weights of this step and the batch shapes.  lr and the AdamW bias
-        corrections are NOT baked (device scalars, FlatAdamW.advance)."""
+        (level mask, delta, anneal), the loss weights of this step, the loss normalisation and the batch shapes.
+        lr and the AdamW bias corrections are NOT baked (device scalars, FlatAdamW.advance), nor is the global
+        sample count of the geometry losses (a device scalar)."""
         sm = self.model.surface_model
         levels = tuple(int(m.active_level) for m in self.model.modules() if hasattr(m, "active_level"))
         weights = tuple(float(w) for w in self.loss_manager.weights(step))
         shapes = tuple((m, tuple(c.shape), tuple(targets[m].shape)) for m, c in coords.items())
+        sc = tuple(sorted(scales.items())) if scales is not None else None
         return (float(sm.numerical_gradients_delta), float(sm.volume_rendering._cos_anneal_ratio), levels, weights, shapes,
-                ops.MLP_PRECISION)
+                sc, ops.MLP_PRECISION)
 
     def train_step_graphed(self, step, coords, targets):
-        """train_step with the ~4000 launches of a step replayed from two CUDA graphs (forward + backward | clip +
+        """train_step with the ~1000 launches of a step replayed from two CUDA graphs (forward + backward | clip +
         AdamW; the NCCL all-reduce sits between them).  A step whose schedule key differs from the previous step's
         runs eagerly (early training: the anneal ratio moves every step); the second step with the same key captures.
-        coords / targets may live in pinned host memory: they are copied into the graphs' static inputs."""
+        coords / targets may live in pinned host memory: they are copied into the graphs' static inputs; the caller
+        may overwrite its pinned buffers once `self.inputs_event` has completed."""
         self.run_callbacks(step)
-        key = self._schedule_key(step, coords, targets)
-        if self._graph is None or self._graph[0] != key:
+        losses, total = self._fb_graphed(step, coords, targets, None, None)
+        self.inputs_event.record()
+        self.all_reduce_gradients()
+        self._optimizer_graphed(step)
+        return losses, total
+
+    def _fb_graphed(self, step, coords, targets, scales, count):
+        """forward + backward of one (micro-)batch from the graph captured for its key; `scales is None`: a whole
+        step's batch (gradients overwrite the flat buffers), otherwise one shard (gradients accumulate)."""
+        accumulate = scales is not None
+        key = self._schedule_key(step, coords, targets, scales)
+        g = self._graphs.get(key)
+        if g is None:
             if self._last_key != key:
                 self._last_key = key
-                self._graph = None
                 dc = {m: c.to(self.device, non_blocking=True) for m, c in coords.items()}
                 dt = {m: t.to(self.device, non_blocking=True) for m, t in targets.items()}
-                losses, total = self.forward_backward(dc, dt, step)
-                self.all_reduce_gradients()
-                self.optimizer_step(step)
-                return losses, total
-            self._capture(key, step, coords, targets)
-        _, sc, st, g_fb, g_opt, losses, total = self._graph
+                return self.forward_backward(dc, dt, step, scales, count, accumulate)
+            g = self._capture(key, step, coords, targets, scales, count)
+        sc, st, scount, g_fb, losses, total = g
         for m in sc:
             sc[m].copy_(coords[m], non_blocking=True)
             st[m].copy_(targets[m], non_blocking=True)
+        if scount is not None:
+            scount.copy_(count)
+        g_fb.replay()
+        return losses, total
+
+    def _optimizer_graphed(self, step):
         f = multistep_warmup_factor(step, self.max_num_iterations)
         for opt in self.optimizers.values():
             opt.advance(lr_factor=f)
-        g_fb.replay()
-        self.all_reduce_gradients()
-        g_opt.replay()
-        return losses, total
+        if self._g_opt is None:
+            self._g_opt = torch.cuda.CUDAGraph()
+            # warm-up outside the capture (cudaFuncSetAttribute etc.), on values that are restored afterwards
+            with torch.cuda.graph(self._g_opt, pool=self._pool):
+                for opt in self.optimizers.values():
+                    opt.step_dev()
+            if self._pool is None:
+                self._pool = self._g_opt.pool()
+        self._g_opt.replay()
 
-    def _capture(self, key, step, coords, targets):
+    def _capture(self, key, step, coords, targets, scales, count):
         from . import _lib
+        accumulate = scales is not None
         sc = {m: torch.empty(c.shape, dtype=c.dtype, device=self.device) for m, c in coords.items()}
         st = {m: torch.empty(t.shape, dtype=t.dtype, device=self.device) for m, t in targets.items()}
+        scount = torch.empty_like(count) if count is not None else None
         for m in sc:
             sc[m].copy_(coords[m])
             st[m].copy_(targets[m])
+        if scount is not None:
+            scount.copy_(count)
         # warm-up on a side stream (torch's whole-network-capture recipe): first-use initialisation
-        # (cudaFuncSetAttribute, constant caches) happens outside the capture
+        # (cudaFuncSetAttribute, constant caches) happens outside the capture.  Its gradients must not count twice:
+        # the flat buffers are saved and restored around it when this capture belongs to an accumulating step.
+        saved = [opt.grad.clone() for opt in self.optimizers.values()] if accumulate else None
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            self.forward_backward(sc, st, step)
+            self.forward_backward(sc, st, step, scales, scount, accumulate)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
+        if saved is not None:
+            for opt, g in zip(self.optimizers.values(), saved):
+                opt.grad.copy_(g)
+            del saved
+        if len(self._graphs) >= 4:              # a captured step owns its activations: keep the cache small
+            self._graphs.pop(next(iter(self._graphs)))
         l0 = _lib.launch_count()
         g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_fb):
-            losses, total = self.forward_backward(sc, st, step)
-        g_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_opt, pool=g_fb.pool()):
-            for opt in self.optimizers.values():
-                opt.step_dev()
+        # all graphs of this pipeline share ONE memory pool: they are replayed one after the other on one stream and
+        # none reads another's outputs after a later replay (the losses are consumed right behind each replay)
+        with torch.cuda.graph(g_fb, pool=self._pool):
+            losses, total = self.forward_backward(sc, st, step, scales, scount, accumulate)
+        if self._pool is None:
+            self._pool = g_fb.pool()
         self.graph_launches = _lib.launch_count() - l0
-        self._graph = (key, sc, st, g_fb, g_opt, losses, total)
+        torch.cuda.synchronize(self.device)
+        if accumulate:
+            # the capture itself did not execute: replaying is the caller's job (it returns through the normal path)
+            pass
+        self._graphs[key] = (sc, st, scount, g_fb, losses, total)
+        return self._graphs[key]

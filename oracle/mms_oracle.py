@@ -318,7 +318,8 @@ TAPS = torch.tensor([[1., -1, -1], [-1, -1, 1], [-1, 1, -1], [1, 1, 1]])
 
 def taps_gradients(sdf_c, sdf_t, delta, want_hessian=True):
     """sdf_c [n,1], sdf_t [4,n,1]; delta = numerical_gradients_delta / sqrt(3) (python float)."""
-    g = (TAPS[0] * sdf_t[0] + TAPS[1] * sdf_t[1] + TAPS[2] * sdf_t[2] + TAPS[3] * sdf_t[3]) / (4.0 * delta)
+    T = TAPS.to(sdf_t.device)
+    g = (T[0] * sdf_t[0] + T[1] * sdf_t[1] + T[2] * sdf_t[2] + T[3] * sdf_t[3]) / (4.0 * delta)
     h = None
     if want_hessian:
         hxx = ((sdf_t[0] + sdf_t[1] + sdf_t[2] + sdf_t[3]) / 2.0 - 2 * sdf_c) / delta ** 2
@@ -502,7 +503,7 @@ class GridModelOracle:
         pos = (oi[:, None] + di[:, None] * starts).reshape(-1, 3)
         sdf, geo = self.sdf_field(pos)
         delta = self.delta / np.sqrt(3)
-        sdf_t = torch.stack([self.sdf_field(pos + TAPS[i] * delta)[0] for i in range(4)], 0)
+        sdf_t = torch.stack([self.sdf_field(pos + TAPS[i].to(pos.device) * delta)[0] for i in range(4)], 0)
         want_h = self.training and c["compute_hessian"]
         g, hess, normals = taps_gradients(sdf, sdf_t, delta, want_h)
         g3, n3 = g.view(-1, s, 3), normals.view(-1, s, 3)

@@ -78,3 +78,28 @@ def mlp_precision(request):
     ops.set_mlp_precision(request.param)
     yield request.param
     ops.set_mlp_precision(old)
+
+
+def assert_close_elementwise(a, b, rtol, atol, what=""):
+    """|a - b| <= rtol * |b| + atol for EVERY element (a relative band with an absolute floor), unlike assert_close
+    whose band is scaled by max|b|."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    excess = (a - b).abs() - (rtol * b.abs() + atol)
+    worst = float(excess.max()) if a.numel() else 0.0
+    assert worst <= 0, f"{what}: an element misses |a-b| <= {rtol}*|b| + {atol} by {worst:.3e} (max abs err {float((a - b).abs().max()):.3e})"
+
+
+_MEASURED = os.path.join(ROOT, "gpurun_out", "parity_measured.jsonl")
+
+
+def record_error(test, quantity, err, band):
+    """Logs the MEASURED error of a parity check next to its band: printed (pytest -rP shows it) and appended to
+    gpurun_out/parity_measured.jsonl when that directory exists (copied to profiles/ and quoted in README)."""
+    import json
+    line = json.dumps({"test": test, "quantity": quantity, "measured": float(err), "band": float(band)})
+    print("[parity]", line)
+    d = os.path.dirname(_MEASURED)
+    if os.path.isdir(d):
+        with open(_MEASURED, "a") as fh:
+            fh.write(line + "\n")

@@ -1,74 +1,140 @@
-"""CPU, gloo, world size 2: the multi-GPU scheme of DESIGN.md §6 — rays sharded across ranks, parameters
-replicated, ONE flat gradient all-reduce (mean) — reproduces the single-process gradient.  The arithmetic on each
-rank is the CPU oracle here (no GPU in this container); the sharding / all-reduce / flat-buffer logic is the
-product's (`pipelines.FlatAdamW`-style flat gradient, `all_reduce_gradients` semantics)."""
+"""CPU, gloo, world size 2: the multi-GPU scheme of DESIGN.md §6 ("strong" mode) — ONE global ray batch
+split contiguously over the ranks by the product's `pipelines.ShardPlan` (ragged modality counts, micro-batches on
+each rank), every loss normalised by the GLOBAL count, gradients accumulated over micro-batches in a flat buffer and
+combined by the product's `pipelines.all_reduce_flat` (one summing all-reduce) — reproduces the gradient of the
+unsharded batch.  Also the "weak" mode (per-rank mean losses, summing all-reduce, 1 / world size folded into the
+optimizer's gradient read = FlatAdamW.prescale).  The arithmetic of a shard is the CPU oracle here (there is no GPU in
+this container; the same plan drives the CUDA path in tests/test_gpu_model.py::test_sharded_*)."""
 import os
+import socket
 import sys
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+COUNTS = {"mono": 7, "rgb": 5}            # ragged on purpose: 7 does not split evenly over 2 ranks x 2 micro-batches
 
 
-def _loss_and_flat_grad(rank, world):
+def _setup():
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import mms_oracle as O
     from multimodalstudio_b200.models import build_model
-    mods = {"mono": 1}
+    mods = {"mono": 1, "rgb": 3}
     model = build_model("grid_raw", modalities=mods, log2_hashmap_size=8, num_samples=8, num_samples_importance=8, bg_samples=4, seed=3)
     params = [p for p in model.parameters()]
     sd = {k: v for k, v in model.state_dict(keep_vars=True).items()}
     orc = O.GridModelOracle(sd, O.default_cfg(modalities=mods, log2_hashmap_size=8, num_samples=8, num_samples_importance=8, bg_samples=4))
-    orc.cfg["num_upsample_steps"] = 4
     orc.training = False
     orc.set_schedule_state(16, 2.0 / 16, 1.0)     # wide taps: keeps the finite-difference amplification of fp32 noise small
     g = torch.Generator().manual_seed(5)
-    n = 8
-    o = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1) * 2.5
-    d = torch.nn.functional.normalize(-o + 0.2 * torch.randn(n, 3, generator=g), dim=-1)
-    up = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
-    tgt = torch.rand(n, 1, generator=g)
-    lo, hi = rank * n // world, (rank + 1) * n // world          # contiguous shard of the ray batch
-    out = orc.forward_modality("mono", o[lo:hi], d[lo:hi], up[lo:hi], None)
-    loss = (out["mono"] - tgt[lo:hi]).abs().mean()               # per-rank mean; ranks are averaged by the all-reduce
-    loss.backward()
-    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
-    return loss.detach(), flat
+    rays, tgt = {}, {}
+    for m, n in COUNTS.items():
+        o = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1) * 2.5
+        d = torch.nn.functional.normalize(-o + 0.2 * torch.randn(n, 3, generator=g), dim=-1)
+        up = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+        rays[m] = torch.cat([o, d, up], -1)
+        tgt[m] = torch.rand(n, mods[m], generator=g)
+    return O, orc, params, rays, tgt
+
+
+def _flat_grad_of_plan(O, orc, params, rays, tgt, plan, geometry_count):
+    """Runs every micro-batch of `plan` through the oracle with the product's loss normalisation and accumulates the
+    gradients in one flat buffer (what FlatAdamW.gather_grads(accumulate=True) does on the device)."""
+    n_flat = sum(p.numel() for p in params)
+    flat, total_sum = torch.zeros(n_flat), 0.0
+    for j in range(len(plan)):
+        part, tpart, scales = plan.slice(j, rays), plan.slice(j, tgt), plan.loss_scales(j)
+        total, grads = 0.0, []
+        for m in COUNTS:
+            if part[m].shape[0] == 0:
+                continue
+            out = orc.forward_modality(m, part[m][:, 0:3], part[m][:, 3:6], part[m][:, 6:9], None)
+            total = total + scales[m] * (out[m] - tpart[m]).abs().mean()            # mean x n_micro / n_global
+            grads.append(out["gradients"])
+        g = torch.cat(grads, 0)
+        eik_sum = ((g.norm(dim=-1) - 1.0) ** 2).sum()
+        total = total + 0.1 * eik_sum / geometry_count                              # local sum / GLOBAL count
+        for p in params:
+            p.grad = None
+        total.backward()
+        flat += torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+        total_sum += float(total.detach())
+    return total_sum, flat
+
+
+def _global_count(O, rays):
+    return float(sum(int(O.sphere_collide(r[:, 0:3], r[:, 3:6])[2].sum()) for r in rays.values()) * 16)
 
 
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(2)
-    loss, flat = _loss_and_flat_grad(rank, world)
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)                  # one flat all-reduce, then the mean (DDP semantics)
-    flat /= world
-    dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+    from multimodalstudio_b200.pipelines import ShardPlan, all_reduce_flat
+    O, orc, params, rays, tgt = _setup()
+    plan = ShardPlan(COUNTS, world, rank, max_rays_per_micro=4)
+    assert len(plan) == 2
+    # the global in-sphere sample count: local count, summed over the ranks (as RawPipeline.train_step_sharded does)
+    local = plan.local_slice(rays)
+    cnt = torch.tensor([_global_count(O, local)])
+    all_reduce_flat(cnt)
+    total, flat = _flat_grad_of_plan(O, orc, params, rays, tgt, plan, float(cnt))
+    all_reduce_flat(flat)                                      # the ONE data-path collective: a summing all-reduce
+    t = torch.tensor([total])
+    all_reduce_flat(t)
     if rank == 0:
-        q.put((loss / world, flat))
+        q.put((float(t), flat, float(cnt)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_sharded_rays_plus_allreduce_equal_single_process():
+def test_sharded_global_batch_plus_allreduce_equals_single_process():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    import socket
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    loss2, flat2 = q.get(timeout=240)
+    loss2, flat2, cnt2 = q.get(timeout=300)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     torch.set_num_threads(2)
-    loss1, flat1 = _loss_and_flat_grad(0, 1)
-    assert abs(float(loss1) - float(loss2)) < 1e-6
+    sys.path.insert(0, ROOT)
+    from multimodalstudio_b200.pipelines import ShardPlan
+    O, orc, params, rays, tgt = _setup()
+    cnt1 = _global_count(O, rays)
+    assert cnt1 == cnt2
+    loss1, flat1 = _flat_grad_of_plan(O, orc, params, rays, tgt, ShardPlan(COUNTS), cnt1)      # one rank, one batch
+    assert abs(loss1 - loss2) < 1e-6 * max(1.0, abs(loss1)), (loss1, loss2)
     err = float((flat1 - flat2).abs().max() / flat1.abs().max())
     assert err < 1e-4, err       # equal up to fp32 reassociation (different batch shapes pick different BLAS kernels)
+
+
+def test_shard_plan_covers_every_ray_once():
+    sys.path.insert(0, ROOT)
+    from multimodalstudio_b200.pipelines import ShardPlan
+    counts = {"rgb": 13108, "infrared": 13107, "mono": 13107, "polarization": 13107, "multispectral": 13107}
+    for world in (1, 2, 3, 4, 8):
+        seen = {m: [] for m in counts}
+        scale_sum = {m: 0.0 for m in counts}
+        for rank in range(world):
+            plan = ShardPlan(counts, world, rank, max_rays_per_micro=8192)
+            assert sum(b - a for a, b in plan.local.values()) <= -(-65536 // world) + len(counts)
+            for j in range(len(plan)):
+                assert sum(b - a for a, b in plan.micro[j].values()) <= 8192
+                for m, (a, b) in plan.micro[j].items():
+                    seen[m] += list(range(a, b))
+                    scale_sum[m] += plan.loss_scales(j)[m]
+        for m, n in counts.items():
+            assert seen[m] == list(range(n))
+            assert abs(scale_sum[m] - 1.0) < 1e-12
+    # the bench's even case: every rank and micro-batch has the same shape (one CUDA-graph key)
+    even = {m: 13112 for m in counts}
+    shapes = {tuple(sorted((m, b - a) for m, (a, b) in mb.items())) for world in (1, 2, 4, 8) for r in range(world)
+              for mb in ShardPlan(even, world, r, max_rays_per_micro=8195).micro}
+    assert len(shapes) == 1
