@@ -149,10 +149,13 @@ int mmsb_linear_pack_weight(const float* w, int64_t ldw, int32_t out_dim, int32_
 int mmsb_linear_fwd_tc(const float* x, int64_t ldx, const float* packed_w, const float* b, float* y, int64_t ldy,
                        int64_t n, int32_t in_dim, int32_t out_dim, int32_t act, float act_param, int32_t precision,
                        mmsb_stream_t stream);
-/* dx = dz W (* act_prev'(y_prev) when y_prev != NULL) with packed_wt = pack(W, transpose = 1). */
+/* dx = dz W (* act_prev'(y_prev) when y_prev != NULL) with packed_wt = pack(W, transpose = 1);
+ * accumulate != 0: dx += ... (a second gradient path into the same rows, e.g. the geometry-feature path of the SDF
+ * network's centre rows on top of the sdf-head path that covers every row). */
 int mmsb_linear_bwd_data_tc(const float* dz, int64_t lddz, const float* packed_wt, float* dx, int64_t lddx,
                             const float* y_prev, int64_t ld_yprev, int32_t act_prev, float act_prev_param,
-                            int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision, mmsb_stream_t stream);
+                            int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision, int32_t accumulate,
+                            mmsb_stream_t stream);
 /* dw[out,in] += dz^T x, db[out] += sum_n dz (db may be NULL); split over n, fp32 reductions in the L2. */
 int mmsb_linear_bwd_weight_tc(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw, float* db,
                               int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision, mmsb_stream_t stream);

@@ -305,6 +305,7 @@ struct EpiArgs {
   const float* head_w; const float* head_b; float* head_out;
   // dgrad with a rank-1 term: (acc + r1_d[row] * r1_w[col]) * act'(yprev)
   const float* r1_d; const float* r1_w;
+  int accumulate;                            // dgrad: C += result instead of C = result
 };
 
 template <int ACT>
@@ -431,6 +432,13 @@ __device__ __forceinline__ void epilogue_rows_in(const EpiArgs& e, const float* 
       }
     }
     if (dst != nullptr) {
+      if (EPI == EPI_DGRAD && e.accumulate) {
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const float4 c = *reinterpret_cast<const float4*>(dst + (i0 + j) * step);
+          x[j].x += c.x; x[j].y += c.y; x[j].z += c.z; x[j].w += c.w;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < G; ++j) *reinterpret_cast<float4*>(dst + (i0 + j) * step) = x[j];
     }
@@ -487,12 +495,17 @@ __device__ __forceinline__ void epilogue_rows_edge(const EpiArgs& e, const float
       if (col + 2 < e.N) atomicAdd(dst + 2 * cs, x.z);
       if (col + 3 < e.N) atomicAdd(dst + 3 * cs, x.w);
     } else if (vec_ok && full) {
+      if (EPI == EPI_DGRAD && e.accumulate) {
+        const float4 c = *reinterpret_cast<const float4*>(dst);
+        x.x += c.x; x.y += c.y; x.z += c.z; x.w += c.w;
+      }
       *reinterpret_cast<float4*>(dst) = x;
     } else {
-      dst[0] = x.x;
-      if (col + 1 < e.N) dst[1] = x.y;
-      if (col + 2 < e.N) dst[2] = x.z;
-      if (col + 3 < e.N) dst[3] = x.w;
+      const bool acc = EPI == EPI_DGRAD && e.accumulate;
+      dst[0] = acc ? dst[0] + x.x : x.x;
+      if (col + 1 < e.N) dst[1] = acc ? dst[1] + x.y : x.y;
+      if (col + 2 < e.N) dst[2] = acc ? dst[2] + x.z : x.z;
+      if (col + 3 < e.N) dst[3] = acc ? dst[3] + x.w : x.w;
     }
   }
 }
@@ -604,6 +617,10 @@ __device__ __forceinline__ void epilogue_chunk_frag(const EpiArgs& e, const uint
       }
       if (e.C != nullptr && row < e.M) {
         float* dst = e.C + row * e.ldc + col;
+        if (EPI == EPI_DGRAD && e.accumulate) {
+          x0 += dst[0];
+          if (two) x1 += dst[1];
+        }
         if (two && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
           *reinterpret_cast<float2*>(dst) = make_float2(x0, x1);
         } else {
@@ -1886,12 +1903,13 @@ static int rows_fwd(const float* x, int64_t ldx, const float* packed_w, const fl
 static int rows_dgrad(const float* a, int64_t lda, const float* packed_wt, float* dx, int64_t lddx, const float* y_prev,
                       int64_t ld_yprev, int act_prev, float act_prev_param, int64_t n, int in_dim, int out_dim,
                       int precision, const float* r1_d, const float* r1_w, const float* hd, const float* hw, int hact,
-                      float hact_param, cudaStream_t stream, const char* what) {
+                      float hact_param, cudaStream_t stream, const char* what, int accumulate = 0) {
   tc::RowsArgs g{};
   g.A = a; g.lda = lda; g.M = n; g.K = out_dim; g.Bp = packed_wt; g.N = in_dim;
   g.epi.C = dx; g.epi.ldc = lddx; g.epi.M = n; g.epi.N = in_dim;
   g.epi.yprev = y_prev; g.epi.ld_yprev = ld_yprev; g.epi.act_prev = act_prev; g.epi.act_prev_param = act_prev_param;
   g.epi.r1_d = r1_d; g.epi.r1_w = r1_w;
+  g.epi.accumulate = accumulate;
   g.epi.direct = epilogue_mode();
   g.hd = hd; g.hw = hw; g.hact = hact; g.hact_param = hact_param;
   g.n_tiles = int(ceil_div(tc::pad16(in_dim), tc::NT)); g.nkb = int(ceil_div(out_dim, tc::TK));
@@ -1952,13 +1970,14 @@ extern "C" int mmsb_linear_fwd_head_tc(const float* x, int64_t ldx, const float*
 
 extern "C" int mmsb_linear_bwd_data_tc(const float* dz, int64_t lddz, const float* packed_wt, float* dx, int64_t lddx,
                                        const float* y_prev, int64_t ld_yprev, int32_t act_prev, float act_prev_param,
-                                       int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision, mmsb_stream_t stream) {
+                                       int64_t n, int32_t in_dim, int32_t out_dim, int32_t precision, int32_t accumulate,
+                                       mmsb_stream_t stream) {
   MMSB_REQUIRE(dz && packed_wt && dx, "linear_bwd_data_tc: null pointer");
   MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && lddz >= out_dim && lddx >= in_dim, "linear_bwd_data_tc: bad shape");
   MMSB_REQUIRE(valid_precision(precision), "linear_bwd_data_tc: precision must be 1 or 3, got %d", precision);
   if (n == 0) return MMSB_OK;
   return rows_dgrad(dz, lddz, packed_wt, dx, lddx, y_prev, ld_yprev, act_prev, act_prev_param, n, in_dim, out_dim, precision,
-                    nullptr, nullptr, nullptr, nullptr, 0, 0.f, as_stream(stream), "linear_bwd_data_tc");
+                    nullptr, nullptr, nullptr, nullptr, 0, 0.f, as_stream(stream), "linear_bwd_data_tc", accumulate != 0);
 }
 
 extern "C" int mmsb_linear_bwd_data_rank1_tc(const float* dz, int64_t lddz, const float* packed_wt, float* dx, int64_t lddx,

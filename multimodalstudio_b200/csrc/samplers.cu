@@ -8,6 +8,7 @@
 // cumprod accumulate sequentially in double like ATen's CPU kernels (verified against torch 2.11);
 // the only ulp-level differences left are expf inside the sigmoid and torch.sum's vector-lane order.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mmsb {
 
@@ -186,6 +187,145 @@ __global__ void __launch_bounds__(128) neus_upsample_kernel(const float* __restr
   mb[m + k] = fmaxf(b[m], nb[k]);
 }
 
+// ---- the same round, one WARP per ray ----------------------------------------------------------------------------
+// Lane l owns the elements l, l + 32, ... of the ray; a row's bins / cdf / new bins live in shared memory (coalesced
+// global loads and stores).  cumprod and cumsum are warp scans in double with a carry between 32-element chunks: the
+// reference's sequential double accumulation re-associated, i.e. equal before the cast back to float except for
+// double-rounding ties (probability ~2^-29 per value).  searchsorted: one lane per query, binary search in shared
+// memory.  Sorted merge: every element's output slot is its rank (old first on ties, ray_samplers.py:46-53).
+__device__ __forceinline__ double warp_scan_prod_f64(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v *= t;
+  }
+  return v;
+}
+__device__ __forceinline__ double warp_scan_sum_f64(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+// number of elements of the sorted row[0..m) that are < v
+__device__ __forceinline__ int lower_bound(const float* __restrict__ row, int m, float v) {
+  int lo = 0, hi = m;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (row[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+constexpr int kUpsampleWarps = 8;
+
+__global__ void __launch_bounds__(kUpsampleWarps * 32) neus_upsample_warp_kernel(
+    const float* __restrict__ bins, const float* __restrict__ sdf, const float* __restrict__ u,
+    const float* __restrict__ nears, const float* __restrict__ fars, float inv_s, float hist_pad, float eps, int m, int k,
+    float* __restrict__ cdf_ws, int64_t* __restrict__ inds_out, float* __restrict__ new_bins,
+    float* __restrict__ merged_bins, int64_t* __restrict__ merged_index, int64_t n) {
+  extern __shared__ float sm_up[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = int64_t(blockIdx.x) * kUpsampleWarps + warp;
+  if (r >= n) return;                                   // warp-uniform; no block-level synchronisation below
+  const int ne = m + 1;
+  float* s_b = sm_up + warp * (2 * ne + k + 1);         // bin edges [ne]
+  float* s_c = s_b + ne;                                // weights, then the cdf [ne]
+  float* s_nb = s_c + ne;                               // new bins [k + 1]
+  const float* b = bins + r * ne;
+  const float* sd = sdf + r * m;
+  for (int j = lane; j < ne; j += 32) s_b[j] = b[j];
+  __syncwarp();
+  const float nr = nears[r], fr = fars[r];
+
+  // --- alphas with fixed inv_s + transmittance weights (ray_samplers.py:516-551, rays.py:201-217)
+  double carry_t = 1.0, wsum = 0.0;
+  float carry_cos = 0.f;
+  for (int base = 0; base < m; base += 32) {
+    const int j = base + lane;
+    const bool valid = j < m - 1;
+    float cosv = 0.f, delta = 0.f, mid = 0.f;
+    if (valid) {
+      delta = __fsub_rn(spacing_to_euclid(s_b[j + 1], nr, fr, MMSB_SPACING_UNIFORM),
+                        spacing_to_euclid(s_b[j], nr, fr, MMSB_SPACING_UNIFORM));
+      const float ps = sd[j], ns = sd[j + 1];
+      mid = __fmul_rn(__fadd_rn(ps, ns), 0.5f);
+      cosv = __fdiv_rn(__fsub_rn(ns, ps), __fadd_rn(delta, 1e-5f));
+    }
+    float prev_cos = __shfl_up_sync(0xffffffffu, cosv, 1);
+    if (lane == 0) prev_cos = carry_cos;
+    carry_cos = __shfl_sync(0xffffffffu, cosv, 31);
+    float alpha = 0.f;
+    if (valid) {
+      float c = fminf(prev_cos, cosv);
+      c = fminf(fmaxf(c, -1e3f), 0.f);
+      const float half = __fmul_rn(__fmul_rn(c, delta), 0.5f);
+      const float pc = sigmoidf_(__fmul_rn(__fsub_rn(mid, half), inv_s));
+      const float nc = sigmoidf_(__fmul_rn(__fadd_rn(mid, half), inv_s));
+      alpha = __fdiv_rn(__fadd_rn(__fsub_rn(pc, nc), 1e-5f), __fadd_rn(pc, 1e-5f));
+    }
+    const double f = valid ? double(__fadd_rn(__fsub_rn(1.0f, alpha), 1e-7f)) : 1.0;
+    const double incl = warp_scan_prod_f64(f, lane);
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.0;
+    const double t_j = carry_t * excl;                  // T before sample j
+    carry_t = carry_t * __shfl_sync(0xffffffffu, incl, 31);
+    if (j < m) {
+      // j == m - 1: the zero weight appended at ray_samplers.py:498
+      const float w = valid ? __fmul_rn(alpha, float(t_j)) : 0.f;
+      const float wp = __fadd_rn(w, hist_pad);          // ray_samplers.py:353
+      s_c[j + 1] = wp;
+      wsum += double(wp);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+  // --- pdf / cdf (ray_samplers.py:356-363)
+  float ws = float(wsum);
+  const float padding = fmaxf(__fsub_rn(eps, ws), 0.f);
+  const float padw = __fdiv_rn(padding, float(m));
+  ws = __fadd_rn(ws, padding);
+  double carry = 0.0;
+  if (lane == 0) s_c[0] = 0.f;
+  for (int base = 0; base < m; base += 32) {
+    const int j = base + lane;
+    const double pdf = j < m ? double(__fdiv_rn(__fadd_rn(s_c[j + 1], padw), ws)) : 0.0;
+    const double incl = carry + warp_scan_sum_f64(pdf, lane);
+    carry = __shfl_sync(0xffffffffu, incl, 31);
+    if (j < m) s_c[j + 1] = fminf(1.f, float(incl));
+  }
+  __syncwarp();
+  float* cdf = cdf_ws + r * ne;
+  for (int j = lane; j < ne; j += 32) cdf[j] = s_c[j];
+  // --- stratified inverse-cdf samples (ray_samplers.py:386-403), one lane per query
+  for (int q = lane; q <= k; q += 32) {
+    int ind;
+    const float v = pdf_inverse_one(s_c, s_b, ne, __ldg(u + r * (k + 1) + q), &ind);
+    s_nb[q] = v;
+    new_bins[r * (k + 1) + q] = v;
+    if (inds_out) inds_out[r * (k + 1) + q] = ind;
+  }
+  __syncwarp();
+  // --- sorted merge of the bin starts by rank, old first on ties (ray_samplers.py:46-53)
+  float* mb = merged_bins + r * (m + k + 1);
+  int64_t* mi = merged_index ? merged_index + r * (m + k) : nullptr;
+  for (int ia = lane; ia < m; ia += 32) {
+    const float v = s_b[ia];
+    const int pos = ia + lower_bound(s_nb, k, v);       // new starts strictly below v come first
+    mb[pos] = v;
+    if (mi) mi[pos] = ia;
+  }
+  for (int ib = lane; ib < k; ib += 32) {
+    const float v = s_nb[ib];
+    const int pos = ib + upper_bound(s_b, m, v);        // old starts <= v come first
+    mb[pos] = v;
+    if (mi) mi[pos] = m + ib;
+  }
+  if (lane == 0) mb[m + k] = fmaxf(s_b[m], s_nb[k]);
+}
+
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ a, int m, const float* __restrict__ b2,
                                                           int k, const int64_t* __restrict__ index,
                                                           float* __restrict__ out, int64_t n) {
@@ -254,6 +394,16 @@ extern "C" int mmsb_neus_upsample(const float* bins, const float* sdf, const flo
   MMSB_REQUIRE(n >= 0 && m >= 2 && k >= 1, "neus_upsample: bad sizes m=%d k=%d", m, k);
   if (n == 0) return MMSB_OK;
   MMSB_REQUIRE(bins && sdf && u && nears && fars && cdf_ws && new_bins && merged_bins, "neus_upsample: NULL pointer");
+  // one warp per ray while a row's bins, cdf and new bins fit the block's shared memory (m up to ~700 samples)
+  const size_t smem = size_t(kUpsampleWarps) * (2 * (m + 1) + k + 1) * sizeof(float);
+  static int force_serial = -1;
+  if (force_serial < 0) { const char* e = getenv("MMSB_UPSAMPLE_SERIAL"); force_serial = e ? atoi(e) : 0; }
+  if (smem <= 48 * 1024 && !force_serial) {
+    neus_upsample_warp_kernel<<<(unsigned)ceil_div(n, kUpsampleWarps), kUpsampleWarps * 32, smem, as_stream(stream)>>>(
+        bins, sdf, u, nears, fars, inv_s, histogram_padding, eps, m, k, cdf_ws, inds_out, new_bins, merged_bins,
+        merged_index, n);
+    return check_launch("neus_upsample");
+  }
   neus_upsample_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, as_stream(stream)>>>(
       bins, sdf, u, nears, fars, inv_s, histogram_padding, eps, m, k, cdf_ws, inds_out, new_bins, merged_bins,
       merged_index, n);

@@ -62,14 +62,16 @@ class SDFField(SurfaceField):
                 and mlp.config.out_activation in (None, "None") and self.config.geo_feature_dim is not None
                 and mlp.layers[1].out_features <= 256)
 
-    def forward_split(self, x, n_full: int):
-        """x [n, 3] -> sdf [n, 1] for every row, geo_feature [n_full, G] for the first n_full rows (one network call for
-        the centre evaluations and the finite-difference taps of surface_model.py:129-152)."""
+    def forward_split(self, x, n_full: int, group: int = 1):
+        """x [n, 3] -> sdf [n, 1] for every row, geo_feature [n_full, G] for the full rows: the first n_full ones
+        (`group` = 1) or row 0 of every group of `group` rows (one network call for the centre evaluations and the
+        finite-difference taps of surface_model.py:129-152; see ops.SdfNetFn for why the grouped layout matters)."""
         mlp = self.field.mlp_head
         rows, perm = self.field.assemble_input([self.position_encoding.piece(x)], x)
         weights = [l.weight for l in mlp.layers]
         weights[0] = ops.permuted_columns(weights[0], perm)
-        return ops.sdf_net_forward(rows, n_full, weights, [l.bias for l in mlp.layers], mlp.config.activation, mlp.act_param)
+        return ops.sdf_net_forward(rows, n_full, weights, [l.bias for l in mlp.layers], mlp.config.activation, mlp.act_param,
+                                   group=group)
 
     def forward(self, x, sdf_only: bool = False):
         if self._fused():
@@ -165,8 +167,12 @@ class NeRFField(torch.nn.Module):
         ).setup(input_dim=self.base_field.output_dim, output_dim=1)
 
     def forward(self, x, viewing_direction):
-        x = ops.assemble([self.position_encoding.piece(x) if self.config.use_position_encoding else ops.copy_piece(x)])
-        feature = self.base_field(x)
+        piece = self.position_encoding.piece(x) if self.config.use_position_encoding else ops.copy_piece(x)
+        if hasattr(self.base_field, "feature_grid"):
+            # hash-grid background (preset grid_raw_grid_bg_unbalanced): cat[x, PE(x)[3:], hash(x)] assembled in place
+            feature = self.base_field(pieces=[piece], positions=x)
+        else:
+            feature = self.base_field(ops.assemble([piece]))
         density = self.density_head(feature)
         head_input = ops.assemble([ops.copy_piece(feature),
                                    self.direction_encoding.piece(viewing_direction) if self.config.use_direction_encoding

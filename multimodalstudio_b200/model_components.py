@@ -379,12 +379,17 @@ class SurfaceModel(nn.Module):
         delta = self.numerical_gradients_delta / np.sqrt(3)
         k = ops.const_tensor("taps4", lambda: torch.tensor([[1, -1, -1], [-1, -1, 1], [-1, 1, -1], [1, 1, 1]], dtype=torch.float32),
                              inputs.device)
-        taps = (inputs[None] + k[:, None, :] * delta).reshape(-1, 3)
         if hasattr(self.surface_field, "_fused") and self.surface_field._fused():
-            # centre + taps as one batch through the network (geometry features only for the centre rows)
-            sdf_all, geo_feature = self.surface_field.forward_split(torch.cat([inputs, taps], 0), n)
-            sdf, sdf_t = sdf_all[:n], sdf_all[n:, 0].reshape(4, n)
+            # centre + taps as one batch through the network (geometry features only for the centre rows), a sample's
+            # five evaluations in adjacent rows: row 5 i = centre (offset 0: x + 0 is x), rows 5 i + 1..4 = taps
+            offs = ops.const_tensor("taps4c", lambda: torch.tensor([[0, 0, 0], [1, -1, -1], [-1, -1, 1], [-1, 1, -1], [1, 1, 1]],
+                                                                   dtype=torch.float32), inputs.device)
+            rows = (inputs[:, None, :] + offs[None] * delta).reshape(-1, 3)
+            sdf_all, geo_feature = self.surface_field.forward_split(rows, n, group=5)
+            sdf_all = sdf_all.view(n, 5)
+            sdf, sdf_t = sdf_all[:, :1], sdf_all[:, 1:].t()
         else:
+            taps = (inputs[None] + k[:, None, :] * delta).reshape(-1, 3)
             sdf, geo_feature = self.surface_field(inputs)
             sdf_t = self.surface_field.single_output(taps).reshape(4, n)
         want_h = bool(self.training and self.config.compute_hessian)

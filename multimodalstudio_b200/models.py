@@ -276,6 +276,29 @@ GRID_YAML_MODEL = {
 }
 
 
+# the `pipeline.model` part of confs/grid_raw_rgb_all_views_pol_10_views.yaml (lines 62-101): as above, but the
+# background base field is the preset's hash grid (no `base_field` override)
+GRID_BG_YAML_MODEL = {k: v for k, v in GRID_YAML_MODEL.items() if k != "background_model"}
+GRID_BG_YAML_MODEL["background_model"] = {"background_field": {"head_field": {"hidden_dim": 256, "weight_norm": True}}}
+
+GRID_PRESETS = ("grid", "grid_raw", "grid_unbalanced", "grid_raw_unbalanced")
+GRID_BG_PRESETS = ("grid_raw_grid_bg_unbalanced",)
+
+
+def grid_bg_model_config() -> BaseModelConfig:
+    """ref: method_configs.py:428-445 (preset `grid_raw_grid_bg_unbalanced`): `grid_raw` with the background estimated by
+    a multi-resolution hash grid of radius 2 (+ 3-layer MLP) instead of an MLP, the background modality heads copied from
+    the radiance model's, and 256 background radiance features."""
+    cfg = grid_model_config()
+    cfg.background_model.background_field.base_field = FeatureGridAndMLPConfig(
+        output_dim=256,
+        feature_grid=FeatureGridConfig(encoding=HashEncodingConfig(max_res=1024), coarse_to_fine=True, radius=2),
+        mlp_head=MLPConfig(num_layers=3, out_activation="ReLU"))
+    cfg.background_model.modality_heads = copy.deepcopy(cfg.radiance_model.modality_heads)
+    cfg.background_model.radiance_feature_dim = 256
+    return cfg
+
+
 def build_model(preset: str = "grid_raw", modalities: Optional[Dict[str, int]] = None, yaml_model: Optional[dict] = None,
                 interpolation: str = "Linear", direction_encoding: str = "nerf", log2_hashmap_size: Optional[int] = None,
                 num_samples: Optional[int] = None, num_samples_importance: Optional[int] = None,
@@ -284,10 +307,13 @@ def build_model(preset: str = "grid_raw", modalities: Optional[Dict[str, int]] =
     """Builds the BaseModel of a preset after the YAML overrides, with the tcnn-free substitutions the
     pinned oracle uses (Linear interpolation, NeRF direction encoding).  Construction order and
     RNG consumption match the reference, so the same torch seed gives the same initial parameters."""
-    if preset not in ("grid", "grid_raw", "grid_unbalanced", "grid_raw_unbalanced"):
+    if preset in GRID_PRESETS:
+        cfg, default_yaml = grid_model_config(), GRID_YAML_MODEL
+    elif preset in GRID_BG_PRESETS:
+        cfg, default_yaml = grid_bg_model_config(), GRID_BG_YAML_MODEL
+    else:
         raise ValueError(f"preset '{preset}' is not on the B200 hot path")
-    cfg = grid_model_config()
-    update_config_dict = copy.deepcopy(GRID_YAML_MODEL if yaml_model is None else yaml_model)
+    update_config_dict = copy.deepcopy(default_yaml if yaml_model is None else yaml_model)
 
     class _Holder:  # update_config works on an object with a `model` attribute
         pass
@@ -295,7 +321,10 @@ def build_model(preset: str = "grid_raw", modalities: Optional[Dict[str, int]] =
     holder = _Holder()
     holder.model = cfg
     update_config(holder, {"model": update_config_dict})
-    for fg in (cfg.surface_model.surface_field.field.feature_grid, cfg.radiance_model.radiance_field.base_field.feature_grid):
+    grids = [cfg.surface_model.surface_field.field.feature_grid, cfg.radiance_model.radiance_field.base_field.feature_grid]
+    if hasattr(cfg.background_model.background_field.base_field, "feature_grid"):
+        grids.append(cfg.background_model.background_field.base_field.feature_grid)
+    for fg in grids:
         fg.encoding.interpolation = interpolation
         if log2_hashmap_size is not None:
             fg.encoding.log2_hashmap_size = log2_hashmap_size

@@ -396,13 +396,13 @@ def linear_fwd_tc(x, packed_w, b, out_dim, act, act_param, precision, out=None):
     return out
 
 
-def linear_bwd_data_tc(dz, packed_wt, in_dim, y_prev, act_prev, act_param, precision, out=None):
+def linear_bwd_data_tc(dz, packed_wt, in_dim, y_prev, act_prev, act_param, precision, out=None, accumulate=False):
     n, o = dz.shape
     if out is None:
         out = torch.empty((n, in_dim), device=dz.device, dtype=torch.float32)
     call("mmsb_linear_bwd_data_tc", ptr(dz), _i64(dz.stride(0)), ptr(packed_wt), ptr(out), _i64(out.stride(0)),
          ptr(y_prev), _i64(y_prev.stride(0) if y_prev is not None else 0), _i32(act_prev), _f32(act_param), _i64(n),
-         _i32(in_dim), _i32(o), _i32(precision), stream_ptr())
+         _i32(in_dim), _i32(o), _i32(precision), _i32(int(accumulate)), stream_ptr())
     return out
 
 
@@ -605,20 +605,31 @@ class MLPFn(torch.autograd.Function):
 
 class SdfNetFn(torch.autograd.Function):
     """The SDF network (surface_field.py:99-116, mlp.py:152-171) with its last layer split into the sdf head (output 0)
-    and the geometry features (outputs 1..G):  x [n, in] -> sdf [n, 1] for every row, geo [n_full, G] for the first
-    n_full rows (the centre evaluations; the tap and sampler evaluations keep only the sdf, surface_model.py:143-146).
+    and the geometry features (outputs 1..G):  x [n, in] -> sdf [n, 1] for every row, geo [n_full, G] for the "full"
+    rows (the centre evaluations; the tap and sampler evaluations keep only the sdf, surface_model.py:143-146).
+    Row layout: `group` = 1: the first n_full rows are the full ones; `group` = g > 1: the rows come in groups of g
+    (one sample's centre evaluation followed by its g - 1 finite-difference taps) and row 0 of every group is full
+    (n_full = n / g).  The grouped layout is what SurfaceModel uses: the + / - contributions of a sample's taps to every
+    weight gradient are ~1/(4 delta') larger than their sum, and the tensor core's accumulators TRUNCATE (round toward
+    zero) on every MMA — a systematic error proportional to the running sum.  With a sample's rows adjacent the
+    cancellation happens inside a few MMAs and the running sums stay at the size of the net gradient; with the taps in
+    blocks of their own (round 1) every CTA of the weight-gradient kernel accumulated one sign only and the error was
+    ~200 x the fp32 reference's at a BASELINE batch size (tests/test_gpu_model.py::test_whole_step_at_baseline_size_vs_oracle).
     The sdf head never runs as a layer: its dot product is fused into the epilogue of layer 1 and its backward into the
-    operand producers of layer 1's dgrad / wgrad (mmsb_linear_*_head_tc) — one arithmetic for centre, taps and sampler.
-    args: (x, n_full, act, act_param, W0, b0, W1, b1, W2, b2), two hidden layers."""
+    operand producers of layer 1's dgrad / wgrad (mmsb_linear_*_head_tc) over ALL rows — one arithmetic for centre, taps
+    and sampler; the geometry-feature path of the full rows is a second, additive gradient path (dgrad with accumulate).
+    args: (x, n_full, group, act, act_param, W0, b0, W1, b1, W2, b2), two hidden layers."""
 
     @staticmethod
-    def forward(ctx, x, n_full, act, act_param, w0, b0, w1, b1, w2, b2):
+    def forward(ctx, x, n_full, group, act, act_param, w0, b0, w1, b1, w2, b2):
         prec = MLP_PRECISION
         if prec == 0:
-            raise RuntimeError("SdfNetFn needs the tcgen05 layer path (MLP precision 1 or 3)")
+            raise RuntimeError("SdfNetFn needs the tcgen05 layer path (MLP precision 1, 2 or 3)")
         in_dim = x.shape[-1]
         x2 = _rows(x, in_dim)
         n = x2.shape[0]
+        if n_full > 0 and group > 1 and n_full * group != n:
+            raise ValueError(f"SdfNetFn: {n} rows are not {n_full} groups of {group}")
         ws = [_f(w0), _f(w1), _f(w2)]
         bs = [_f(b0), _f(b1), _f(b2)]
         hid = ws[1].shape[0]
@@ -634,8 +645,9 @@ class SdfNetFn(torch.autograd.Function):
              ptr(bs[2]), ptr(sdf), stream_ptr())
         geo = None
         if n_full > 0:
-            geo = linear_fwd_tc(h1[:n_full], packed_weight(w2, False, prec, rows=(1, g_dim + 1)), bs[2][1:], g_dim, 0, 1.0, prec)
-        ctx.cfg = (n, n_full, act, act_param, prec, in_dim, x.shape)
+            h1c = h1[0::group] if group > 1 else h1[:n_full]
+            geo = linear_fwd_tc(h1c, packed_weight(w2, False, prec, rows=(1, g_dim + 1)), bs[2][1:], g_dim, 0, 1.0, prec)
+        ctx.cfg = (n, n_full, group, act, act_param, prec, in_dim, x.shape)
         if need_grad:
             ctx.save_for_backward(x2, h0, h1, *ws)
             ctx.packed_t = (packed_weight(w0, True, prec) if ctx.needs_input_grad[0] else None, packed_weight(w1, True, prec),
@@ -647,7 +659,7 @@ class SdfNetFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dsdf, dgeo):
-        n, n_full, act, act_param, prec, in_dim, x_shape = ctx.cfg
+        n, n_full, group, act, act_param, prec, in_dim, x_shape = ctx.cfg
         x2, h0, h1, w0, w1, w2 = ctx.saved_tensors
         p0t, p1t, p2t = ctx.packed_t
         dev = x2.device
@@ -656,27 +668,24 @@ class SdfNetFn(torch.autograd.Function):
         dw0, db0, dw1, db1, dw2, db2 = _zeros_many([tuple(w0.shape), (w0.shape[0],), tuple(w1.shape), (hid,), tuple(w2.shape),
                                                     (w2.shape[0],)], dev)
         dz0 = torch.empty((n, hid), device=dev, dtype=torch.float32)
+        # sdf-head path, every row: dz1 = d * w2[0] * act'(h1) is generated in the operand producers, never stored
+        call("mmsb_linear_bwd_weight_head_tc", ptr(h1), _i64(hid), _i32(act), _f32(act_param), ptr(d), ptr(w2), ptr(h0),
+             _i64(hid), ptr(dw1), ptr(db1), ptr(dw2), _i64(n), _i32(hid), _i32(hid), _i32(prec), stream_ptr())
+        db2[0:1] += d.sum()
+        call("mmsb_linear_bwd_data_head_tc", ptr(h1), _i64(hid), _i32(act), _f32(act_param), ptr(d), ptr(w2), ptr(p1t),
+             ptr(dz0), _i64(hid), ptr(h0), _i64(hid), _i32(act), _f32(act_param), _i64(n), _i32(hid), _i32(hid),
+             _i32(prec), stream_ptr())
         if n_full > 0:
+            # geometry-feature path of the full rows (strided views when the rows are grouped), added on top
             dg = torch.zeros((n_full, g_dim), device=dev) if dgeo is None else _rows(dgeo.reshape(n_full, g_dim), g_dim)
-            h1c, h0c, dc = h1[:n_full], h0[:n_full], d[:n_full]
+            if group > 1:
+                h1c, h0c, dz0c = h1[0::group], h0[0::group], dz0[0::group]
+            else:
+                h1c, h0c, dz0c = h1[:n_full], h0[:n_full], dz0[:n_full]
             linear_bwd_weight_tc(dg, h1c, dw2[1:], db2[1:], prec)
-            dz1c = torch.empty((n_full, hid), device=dev, dtype=torch.float32)
-            call("mmsb_linear_bwd_data_rank1_tc", ptr(dg), _i64(dg.stride(0)), ptr(p2t), ptr(dz1c), _i64(hid), ptr(h1c),
-                 _i64(hid), _i32(act), _f32(act_param), _i64(n_full), _i32(hid), _i32(g_dim), _i32(prec), ptr(dc), ptr(w2),
-                 stream_ptr())
-            # the head's own weight / bias gradient from the centre rows (a one-row product)
-            linear_bwd_weight_tc(dc[:, None], h1c, dw2[0:1], db2[0:1], prec)
-            linear_bwd_weight_tc(dz1c, h0c, dw1, db1, prec)
-            linear_bwd_data_tc(dz1c, p1t, hid, h0c, act, act_param, prec, out=dz0[:n_full])
-        if n > n_full:
-            h1t, h0t, dt = h1[n_full:], h0[n_full:], d[n_full:]
-            m = n - n_full
-            call("mmsb_linear_bwd_weight_head_tc", ptr(h1t), _i64(hid), _i32(act), _f32(act_param), ptr(dt), ptr(w2), ptr(h0t),
-                 _i64(hid), ptr(dw1), ptr(db1), ptr(dw2), _i64(m), _i32(hid), _i32(hid), _i32(prec), stream_ptr())
-            db2[0:1] += dt.sum()
-            call("mmsb_linear_bwd_data_head_tc", ptr(h1t), _i64(hid), _i32(act), _f32(act_param), ptr(dt), ptr(w2), ptr(p1t),
-                 ptr(dz0[n_full:]), _i64(hid), ptr(h0t), _i64(hid), _i32(act), _f32(act_param), _i64(m), _i32(hid), _i32(hid),
-                 _i32(prec), stream_ptr())
+            dz1g = linear_bwd_data_tc(dg, p2t, hid, h1c, act, act_param, prec)
+            linear_bwd_weight_tc(dz1g, h0c, dw1, db1, prec)
+            linear_bwd_data_tc(dz1g, p1t, hid, h0c, act, act_param, prec, out=dz0c, accumulate=True)
         linear_bwd_weight_tc(dz0, x2, dw0, db0, prec)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -684,12 +693,12 @@ class SdfNetFn(torch.autograd.Function):
             linear_bwd_data_tc(dz0, p0t, in_dim, None, 0, 1.0, prec, out=dx)
             if tuple(dx.shape) != tuple(x_shape):
                 dx = dx.reshape(x_shape)
-        return dx, None, None, None, dw0, db0, dw1, db1, dw2, db2
+        return dx, None, None, None, None, dw0, db0, dw1, db1, dw2, db2
 
 
-def sdf_net_forward(x, n_full, weights, biases, act: str, act_param: float):
-    return SdfNetFn.apply(x, int(n_full), ACT[act], float(act_param), weights[0], biases[0], weights[1], biases[1], weights[2],
-                          biases[2])
+def sdf_net_forward(x, n_full, weights, biases, act: str, act_param: float, group: int = 1):
+    return SdfNetFn.apply(x, int(n_full), int(group), ACT[act], float(act_param), weights[0], biases[0], weights[1], biases[1],
+                          weights[2], biases[2])
 
 
 def mlp_forward(x, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]], hidden_act: str,

@@ -294,14 +294,18 @@ def golden_losses():
     save("losses", height=H, width=W, **out)
 
 
-def golden_model(tag, level, delta, anneal, rays=10, seed_in=81):
-    """Whole BaseModel.forward + channel select + LossManager + backward of the real reference (grid_raw, 5 modalities)."""
+def golden_model(tag, level, delta, anneal, rays=10, seed_in=81, preset="grid_raw", yaml_name="grid_raw.yaml", modalities=None):
+    """Whole BaseModel.forward + channel select + LossManager + backward of the real reference (default: grid_raw, 5
+    modalities; `gridbg`: preset grid_raw_grid_bg_unbalanced with confs/grid_raw_rgb_all_views_pol_10_views.yaml, RGB +
+    polarization)."""
     from cameras.rays import RayBundle
     from pipelines.raw_pipeline import RawPipeline
-    model, tc = build_reference_model(log2_hashmap_size=12)
+    MODALITY_CHANNELS = modalities or globals()["MODALITY_CHANNELS"]
+    model, tc = build_reference_model(preset=preset, yaml_name=yaml_name, modalities=dict(MODALITY_CHANNELS), log2_hashmap_size=12)
     set_schedule_state(model, level=level, delta=delta, anneal=anneal)
     model.train()
-    out = dict(log2_hashmap_size=12, level=level, delta=delta, anneal=anneal, seed=654824)
+    out = dict(log2_hashmap_size=12, level=level, delta=delta, anneal=anneal, seed=654824, preset=preset,
+               modalities=",".join(MODALITY_CHANNELS))
     H, W = 64, 48
     g = torch.Generator().manual_seed(seed_in)
     inputs, coords, targets, masks_m = {}, {}, {}, {}
@@ -356,6 +360,12 @@ def golden_model(tag, level, delta, anneal, rays=10, seed_in=81):
     save("model_" + tag, height=H, width=W, **out)
 
 
+def golden_gridbg():
+    """BASELINE.json configs[3]: hash-grid background preset, RGB + polarization."""
+    golden_model("gridbg", level=16, delta=2.0 / 1024, anneal=1.0, rays=10, seed_in=181, preset="grid_raw_grid_bg_unbalanced",
+                 yaml_name="grid_raw_rgb_all_views_pol_10_views.yaml", modalities={"rgb": 3, "polarization": 4})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -373,3 +383,4 @@ if __name__ == "__main__":
     golden_losses()
     golden_model("late", level=16, delta=2.0 / 1024, anneal=1.0)
     golden_model("early", level=1, delta=2.0 / 16, anneal=0.0)
+    golden_gridbg()

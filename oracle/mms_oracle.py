@@ -433,10 +433,11 @@ class GridModelOracle:
         m[self.level * self.cfg["features_per_level"]:] = 0
         return m
 
-    def _grid_mlp(self, prefix, inputs, hidden_act, out_act, beta=1.0):
+    def _grid_mlp(self, prefix, inputs, hidden_act, out_act, beta=1.0, radius=None):
         """FeatureGridAndMLP.forward (feature_structures.py:153-169)"""
         feats = hash_encode(inputs[..., :3], self.sd[prefix + ".feature_grid.encoding.hash_table"], self.res,
-                            self.cfg["log2_hashmap_size"], radius=self.cfg["radius"], mask=self._mask())
+                            self.cfg["log2_hashmap_size"], radius=self.cfg["radius"] if radius is None else radius,
+                            mask=self._mask())
         return mlp(self.sd, prefix + ".mlp_head", torch.cat([inputs, feats], -1), 3, hidden_act, out_act, beta)
 
     def sdf_field(self, x):
@@ -483,7 +484,12 @@ class GridModelOracle:
         bdirs = d[:, None].expand(-1, c["bg_samples"], -1).reshape(-1, 3)
         bup = up[:, None].expand(-1, c["bg_samples"], -1).reshape(-1, 3)
         p = "background_model.background_field"
-        feat = mlp(sd, p + ".base_field", nerf_encode(bpos, 6, 0.0, 5), 4, "ReLU", "ReLU")
+        if c.get("bg_grid"):
+            # preset grid_raw_grid_bg_unbalanced (method_configs.py:428-445): hash-grid background field of radius 2,
+            # fed cat[x, PE(x)[3:], hash(x)] (nerf_field.py:92-96 -> feature_structures.py:153-166)
+            feat = self._grid_mlp(p + ".base_field", nerf_encode(bpos, 6, 0.0, 5), "ReLU", "ReLU", radius=c["bg_radius"])
+        else:
+            feat = mlp(sd, p + ".base_field", nerf_encode(bpos, 6, 0.0, 5), 4, "ReLU", "ReLU")
         density = mlp(sd, p + ".density_head.field", feat, 1, "ReLU", "Softplus")
         bfeat = mlp(sd, p + ".head_field", torch.cat([feat, nerf_encode(bdirs, 4, 0.0, 3)], -1), 4, "ReLU", "ReLU")
         bw = density_weights(density.view(-1, c["bg_samples"], 1), bends - bstarts)
@@ -491,10 +497,11 @@ class GridModelOracle:
         bg = {}
         for h in head_list:
             hp = f"background_model.modality_heads.{h}.field"
+            nl = 3 if c.get("bg_grid") else 1         # the grid-background preset copies the radiance heads
             if h == "polarization":
-                v = polarization_post(mlp(sd, hp, bfeat, 1, "ReLU", "None"), bdirs, bup)
+                v = polarization_post(mlp(sd, hp, bfeat, nl, "ReLU", "None"), bdirs, bup)
             else:
-                v = mlp(sd, hp, bfeat, 1, "ReLU", "Sigmoid")
+                v = mlp(sd, hp, bfeat, nl, "ReLU", "Sigmoid")
             bg[h] = torch.sum(bw * v.view(-1, c["bg_samples"], v.shape[-1]), dim=1)
         # surface (surface_model.py:66-127)
         e = spacing_to_euclid(bins, ni, fi)
@@ -564,10 +571,10 @@ class GridModelOracle:
 
 
 def default_cfg(modalities=None, log2_hashmap_size=19, num_samples=32, num_samples_importance=32, bg_samples=16,
-                dir_encoding="nerf"):
+                dir_encoding="nerf", bg_grid=False):
     """confs/grid_raw.yaml over the `grid_raw` preset with the tcnn-free substitutions of SURVEY §8c."""
     return dict(modalities=modalities or {"rgb": 3, "infrared": 1, "mono": 1, "polarization": 4, "multispectral": 9},
                 log2_hashmap_size=log2_hashmap_size, num_levels=16, features_per_level=2, min_res=16, max_res=1024,
                 radius=1.0, radius_collider=1.0, num_samples=num_samples, num_samples_importance=num_samples_importance,
                 num_upsample_steps=4, bg_samples=bg_samples, base_variance=64, dir_encoding=dir_encoding,
-                use_n_dot_v=True, use_reflection_direction=False, compute_hessian=True)
+                use_n_dot_v=True, use_reflection_direction=False, compute_hessian=True, bg_grid=bg_grid, bg_radius=2.0)

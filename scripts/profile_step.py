@@ -1,23 +1,28 @@
 """dev: kernel-level timeline of the graphed train step with torch.profiler (CUPTI activity records, no replay):
 every kernel of the step including torch's glue kernels, summed over `--steps` replays.
 
-    python scripts/profile_step.py --workload grid_raw --steps 3 --out gpurun_out/kernels.txt
+    python scripts/profile_step.py --workload sweep --steps 3 --out gpurun_out/kernels.txt
+
+`sweep` profiles ONE micro-batch per step (8195 rays x 256 samples: the per-GPU share of the 65560-ray global batch at 8
+GPUs, and what a single GPU repeats 8 times per optimizer step).
 """
 import argparse, collections, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 from multimodalstudio_b200.models import MODALITY_CHANNELS
-from multimodalstudio_b200.pipelines import RawPipeline, SyntheticScene
+from multimodalstudio_b200.pipelines import RawPipeline, ShardPlan, SyntheticScene
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--workload", default="grid_raw")
+ap.add_argument("--workload", default="sweep")
 ap.add_argument("--rays", type=int, default=None)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--out", default="gpurun_out/kernels.txt")
 ap.add_argument("--eager", action="store_true")
 args = ap.parse_args()
 wl = dict(bench.WORKLOADS[args.workload])
+if args.workload == "sweep":
+    wl["rays"] = wl["micro"]
 if args.rays:
     wl["rays"] = args.rays
 dev = torch.device("cuda", 0)
@@ -26,7 +31,8 @@ scene = SyntheticScene(mods, bench.split_rays(wl["rays"], wl["modalities"]), raw
 pipe = RawPipeline(mods, scene.cameras, device=dev, raw=wl["raw"], render_all_heads=False, num_samples=wl["n_c"],
                    num_samples_importance=wl["n_i"], bg_samples=wl["bg"])
 batches = [tuple({m: t.to(dev) for m, t in d.items()} for d in scene.sample_batch()) for _ in range(2)]
-step = pipe.train_step if args.eager else pipe.train_step_graphed
+plan = ShardPlan(bench.split_rays(wl["rays"], wl["modalities"]))
+step = lambda i, cs, ts: pipe.train_step_sharded(i, cs, ts, plan, graphed=not args.eager)
 for i in range(3):
     step(bench.BASE_STEP + i, *batches[i % 2])
 torch.cuda.synchronize()

@@ -228,7 +228,7 @@ def test_neus_sampler_golden(mode):
     assert_close(sb, ref, rtol=2e-2, what="neus bins (worst case below one bin width)")
 
 
-@pytest.mark.parametrize("n,m,k", [(1, 32, 8), (333, 40, 8), (5000, 56, 8), (64, 128, 32)])
+@pytest.mark.parametrize("n,m,k", [(1, 32, 8), (333, 40, 8), (5000, 56, 8), (64, 128, 32), (1001, 224, 32), (77, 33, 31), (9, 2, 1)])
 def test_upsample_round_vs_oracle(n, m, k):
     ops = _ops()
     gen = torch.Generator().manual_seed(n * 7 + m)
@@ -258,6 +258,11 @@ def test_upsample_round_vs_oracle(n, m, k):
     cat = torch.cat([bins[:, :-1].to(DEV), new_bins[:, :-1]], -1)
     assert torch.equal(torch.gather(cat, 1, index), merged[:, :-1])
     assert torch.equal(ops.merge_rows(bins[:, :-1].to(DEV), new_bins[:, :-1].contiguous(), index), merged[:, :-1])
+    # the merge is the oracle's (stable: old starts first on ties) when fed the same new bins
+    both = torch.cat([bins[:, :-1].to(DEV), new_bins[:, :-1]], -1)
+    ref_sorted, ref_index = torch.sort(both, dim=-1, stable=True)
+    assert torch.equal(merged[:, :-1], ref_sorted) and torch.equal(index, ref_index)
+    assert torch.equal(merged[:, -1], torch.maximum(bins[:, -1].to(DEV), new_bins[:, -1]))
 
 
 # ---------------------------------------------------------------- ray generation (A1/A2)
@@ -531,17 +536,20 @@ def test_mlp_precision_modes_agree(prec):
         assert_close(a, r, rtol=tol, what=name)
 
 
-@pytest.mark.parametrize("n,n_full", [(5000, 1000), (777, 0), (4096, 4096), (130, 1)])
-def test_sdf_net_fused_head_vs_fp64(n, n_full):
-    """ops.SdfNetFn (sdf head fused into layer 1's epilogue / operand producers, geometry features only for the first
-    n_full rows) against the plain three-layer network in fp64: outputs and every gradient."""
+@pytest.mark.parametrize("n,n_full,group", [(5000, 1000, 1), (777, 0, 1), (4096, 4096, 1), (130, 1, 1), (5000, 1000, 5),
+                                            (1285, 257, 5), (40000, 8000, 5)])
+def test_sdf_net_fused_head_vs_fp64(n, n_full, group):
+    """ops.SdfNetFn (sdf head fused into layer 1's epilogue / operand producers, geometry features only for the full
+    rows: the first n_full ones, or row 0 of every group of `group` rows) against the plain three-layer network in
+    fp64: outputs and every gradient."""
     from multimodalstudio_b200 import ops
     torch.manual_seed(n + n_full)
+    full = slice(0, n_full) if group == 1 else slice(0, None, group)
     x = (torch.randn(n, 72, device=DEV)[:, :71] * 0.5).requires_grad_()
     ws = [(torch.randn(256, 71, device=DEV) * 0.1).requires_grad_(), (torch.randn(256, 256, device=DEV) * 0.06).requires_grad_(),
           (torch.randn(257, 256, device=DEV) * 0.06).requires_grad_()]
     bs = [(torch.randn(o, device=DEV) * 0.1).requires_grad_() for o in (256, 256, 257)]
-    sdf, geo = ops.sdf_net_forward(x, n_full, ws, bs, "Softplus", 100.0)
+    sdf, geo = ops.sdf_net_forward(x, n_full, ws, bs, "Softplus", 100.0, group=group)
     h = x.double()
     for w, b in zip(ws[:2], bs[:2]):
         h = torch.nn.functional.softplus(h @ w.double().T + b.double(), beta=100)
@@ -550,10 +558,10 @@ def test_sdf_net_fused_head_vs_fp64(n, n_full):
     assert geo.shape == (n_full, 256)
     g_sdf = torch.randn(n, 1, device=DEV)
     g_geo = torch.randn(n_full, 256, device=DEV)
-    loss_ref = (out[:, :1] * g_sdf.double()).sum() + (out[:n_full, 1:] * g_geo.double()).sum()
+    loss_ref = (out[:, :1] * g_sdf.double()).sum() + ((out[full, 1:] * g_geo.double()).sum() if n_full else 0.0)
     loss = (sdf * g_sdf).sum() + ((geo * g_geo).sum() if n_full else 0.0)
     if n_full:
-        assert_close(geo, out[:n_full, 1:], rtol=2e-5, what="geo")
+        assert_close(geo, out[full, 1:], rtol=2e-5, what="geo")
     params = [x] + ws + bs
     ref = torch.autograd.grad(loss_ref, params, allow_unused=True)
     got = torch.autograd.grad(loss, params, allow_unused=True)

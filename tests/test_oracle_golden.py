@@ -150,3 +150,38 @@ def test_whole_model(tag):
         elif k.startswith("gradnorm."):
             name = k[9:]
             assert_close(sd[name].grad.norm(), g.t(k), rtol=5e-5, what=k)
+
+
+def test_whole_model_grid_background_preset():
+    """BASELINE.json configs[3]: preset grid_raw_grid_bg_unbalanced (hash-grid background of radius 2, background heads
+    copied from the radiance heads; method_configs.py:428-445) with confs/grid_raw_rgb_all_views_pol_10_views.yaml,
+    RGB + polarization: the host mirror's seeded parameters + the oracle reproduce the reference's step."""
+    from multimodalstudio_b200.models import MOSAICK_PATTERNS, build_model
+    g = load_golden("model_gridbg")
+    mods = {"rgb": 3, "polarization": 4}
+    model = build_model("grid_raw_grid_bg_unbalanced", modalities=mods, log2_hashmap_size=int(g["log2_hashmap_size"]), seed=int(g["seed"]))
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    assert sd["background_model.background_field.base_field.feature_grid.encoding.hash_table"].shape == (16 * 4096, 2)
+    assert sd["background_model.modality_heads.polarization.field.layers.2.bias"].shape == (3,)
+    orc = O.GridModelOracle(sd, O.default_cfg(modalities=mods, log2_hashmap_size=int(g["log2_hashmap_size"]), bg_grid=True))
+    orc.set_schedule_state(int(g["level"]), float(g["delta"]), float(g["anneal"]))
+    outputs, coords, targets = {}, {}, {}
+    for mod in mods:
+        rand = {"uniform": g.t(mod + "_rand_uniform"), "pdf": g.t(mod + "_rand_pdf"), "background": g.t(mod + "_rand_bg")}
+        outputs[mod] = orc.forward_modality(mod, g.t(mod + "_origins"), g.t(mod + "_directions"), g.t(mod + "_up"), rand)
+        coords[mod], targets[mod] = g.t(mod + "_coords"), g.t(mod + "_target")
+        for k in list(mods) + ["normals", "depth", "accumulation", "gradients", "hessians"]:
+            assert_close(outputs[mod][k], g.t(f"{mod}_out_{k}"), rtol=2e-5, what=f"gridbg {mod} {k}")
+    losses, total = orc.loss(outputs, targets, coords, MOSAICK_PATTERNS, float(g["loss_curvature_loss_weight"]))
+    assert_close(total, g.t("loss_total"), what="total loss")
+    total.backward()
+    n_checked = 0
+    for k in g:
+        if k.startswith("grad."):
+            gr = sd[k[5:]].grad if sd[k[5:]].grad is not None else torch.zeros_like(sd[k[5:]])
+            assert_close(gr, g.t(k), rtol=5e-5, atol=1e-9, what=k)
+            n_checked += 1
+        elif k.startswith("gradnorm."):
+            assert_close(sd[k[9:]].grad.norm(), g.t(k), rtol=5e-5, what=k)
+            n_checked += 1
+    assert n_checked > 60
