@@ -73,6 +73,51 @@ class SDFField(SurfaceField):
         return ops.sdf_net_forward(rows, n_full, weights, [l.bias for l in mlp.layers], mlp.config.activation, mlp.act_param,
                                    group=group)
 
+    def forward_with_gradient(self, x):
+        """x [n, 3] -> sdf [n, 1], geo_feature [n, G], d sdf / d x [n, 3] for an MLP field (presets `mlp*`).
+
+        The reference takes the gradient with `torch.autograd.grad(sdf, x, create_graph=True)` (surface_model.py:193-203)
+        and differentiates THROUGH it in the training backward (a double backward).  Here the same quantity is a
+        forward-mode pass: three tangent rows per point (d PE / d x_k) go through the same linear layers (no bias) and are
+        scaled by the activation derivative of every hidden layer, t <- act'(z) * (W t).  It is built from the ordinary
+        differentiable operators (the tensor-core layer kernels + element-wise torch ops), so the training backward is a
+        plain first-order backward of a forward computation: no double backward exists on this path.
+        act'(z) is evaluated from the stored activation: Softplus_beta' = 1 - exp(-beta * softplus(z)), ReLU' = [y > 0]."""
+        import math
+        mlp = self.field
+        if hasattr(mlp, "feature_grid") or not self.config.use_position_encoding:
+            raise NotImplementedError("analytic SDF gradients are implemented for the PE + MLP field of the `mlp*` presets")
+        enc = self.position_encoding
+        n = x.shape[0]
+        pe = enc(x)                                                        # [n, P]
+        # tangents of the encoding: d/dx_k of [x, sin(f x_d), sin(f x_d + pi/2)] (encodings.py:161-182)
+        fr = torch.tensor(enc.freqs, device=x.device, dtype=torch.float32)  # [K]
+        k_ = fr.shape[0]
+        s = x[:, :, None] * fr                                             # [n, 3, K]
+        eye = torch.eye(3, device=x.device, dtype=torch.float32)
+        d_sin = (fr * torch.cos(s))[:, None, :, :] * eye[None, :, :, None]               # [n, k, d, K]
+        d_cos = (fr * torch.cos(s + math.pi / 2.0))[:, None, :, :] * eye[None, :, :, None]
+        parts = ([eye[None].expand(n, 3, 3)] if enc.include_input else []) + [d_sin.reshape(n, 3, 3 * k_), d_cos.reshape(n, 3, 3 * k_)]
+        t_pe = torch.cat(parts, dim=-1).reshape(3 * n, -1)                  # [3 n, P], row 3 i + k = d PE(x_i) / d x_k
+        act, beta = mlp.config.activation, mlp.act_param
+        skips = tuple(mlp.config.skip_connections)
+        nl = len(mlp.layers)
+        h, t = pe, t_pe
+        for i, layer in enumerate(mlp.layers):
+            if i in skips:
+                h = torch.cat([h, pe], -1) / math.sqrt(2)
+                t = torch.cat([t, t_pe], -1) / math.sqrt(2)
+            last = i == nl - 1
+            h = ops.mlp_forward(h, [layer.weight], [layer.bias], act, mlp.config.out_activation if last else act, beta)
+            t = ops.mlp_forward(t, [layer.weight], [None], act, "None", beta, n_out_used=1 if last else None)
+            if not last:
+                d_act = (1.0 - torch.exp(-beta * h)) if act == "Softplus" else (h > 0).to(h.dtype)
+                t = (d_act[:, None, :] * t.view(n, 3, -1)).reshape(3 * n, -1)
+        if mlp.config.out_activation not in (None, "None"):
+            raise NotImplementedError("analytic SDF gradients need a linear output layer")
+        sdf, geo = h[:, :1], h[:, 1:]
+        return sdf, geo, t.view(n, 3)
+
     def forward(self, x, sdf_only: bool = False):
         if self._fused():
             x2 = x.reshape(-1, 3)

@@ -362,11 +362,10 @@ class SurfaceModel(nn.Module):
         self.spatial_distortion = self.config.spatial_distortion.setup() \
             if self.config.spatial_distortion is not None else None
         self.numerical_gradients_delta = None
-        if not self.config.use_numerical_gradients:
-            raise NotImplementedError(
-                "autograd SDF gradients (presets `mlp*`, surface_model.py:193-203) need a double backward that "
-                "the B200 path does not provide yet; use use_numerical_gradients=True")
-        if self.config.numerical_gradient_taps != 4:
+        if not self.config.use_numerical_gradients and self.config.compute_hessian:
+            raise NotImplementedError("Hessians of the autograd SDF gradient (a third-order backward) are not on the B200 path; "
+                                      "the shipped `mlp*` presets set compute_hessian=False")
+        if self.config.use_numerical_gradients and self.config.numerical_gradient_taps != 4:
             raise ValueError("Invalid number of taps for numerical gradients. Must be 4.")
 
     def forward(self, ray_samples: RaySamples, return_weights=True, mask=None):
@@ -375,6 +374,8 @@ class SurfaceModel(nn.Module):
         if self.spatial_distortion is not None:
             inputs = self.spatial_distortion(inputs)
         n = inputs.shape[0]
+        if not self.config.use_numerical_gradients:
+            return self._forward_analytic(ray_samples, inputs, shape, return_weights, mask)
         # 4 tetrahedron taps, sdf only (surface_model.py:138-146)
         delta = self.numerical_gradients_delta / np.sqrt(3)
         k = ops.const_tensor("taps4", lambda: torch.tensor([[1, -1, -1], [-1, -1, 1], [-1, 1, -1], [1, 1, 1]], dtype=torch.float32),
@@ -407,6 +408,22 @@ class SurfaceModel(nn.Module):
             outputs["weights"] = self.volume_rendering(ray_samples, sdf, gradients=gradients, mask=mask)
         return outputs
 
+    def _forward_analytic(self, ray_samples, inputs, shape, return_weights, mask):
+        """use_numerical_gradients=False (presets `mlp*`, surface_model.py:193-203): d sdf / d x by a forward-mode pass
+        through the MLP (SDFField.forward_with_gradient) instead of autograd.grad(create_graph=True)."""
+        sdf, geo_feature, gradients = self.surface_field.forward_with_gradient(inputs)
+        normals = torch.nn.functional.normalize(gradients, p=2, dim=-1)
+        sdf = sdf.reshape(*shape, -1)
+        gradients = gradients.reshape(*shape, -1)
+        outputs = {
+            "sdf": sdf, "normals": normals.reshape(*shape, -1), "gradients": gradients, "geo_feature": geo_feature,
+            "hessians": None, "inputs": inputs, "sampled_sdf": None,
+            "inv_s": 1.0 / self.volume_rendering.density_fn.variance_network.get_inv_variance(),
+        }
+        if return_weights:
+            outputs["weights"] = self.volume_rendering(ray_samples, sdf, gradients=gradients, mask=mask)
+        return outputs
+
     def get_sdf(self, ray_samples: RaySamples):
         shape = ray_samples.shape
         inputs = ray_samples.frustums.get_start_positions().reshape(-1, 3)
@@ -426,7 +443,7 @@ class SurfaceModel(nn.Module):
     def get_training_callbacks(self, training_callback_attributes):
         callbacks = self.volume_rendering.get_training_callbacks(training_callback_attributes) + \
             self.surface_field.get_training_callbacks(training_callback_attributes)
-        if self.config.use_numerical_gradients:
+        if self.config.use_numerical_gradients and hasattr(self.surface_field.field, "feature_grid"):
             fg = self.surface_field.field.feature_grid
             enc = fg.config.encoding
             max_it = training_callback_attributes.trainer.max_num_iterations

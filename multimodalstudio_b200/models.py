@@ -281,7 +281,19 @@ GRID_YAML_MODEL = {
 GRID_BG_YAML_MODEL = {k: v for k, v in GRID_YAML_MODEL.items() if k != "background_model"}
 GRID_BG_YAML_MODEL["background_model"] = {"background_field": {"head_field": {"hidden_dim": 256, "weight_norm": True}}}
 
+# the `pipeline.model` part of confs/mlp.yaml == confs/mlp_raw.yaml (lines 59-88)
+MLP_YAML_MODEL = {
+    "ray_sampler": {"num_samples": 32, "num_samples_importance": 32},
+    "background_ray_sampler": {"num_samples": 16},
+    "surface_model": {"use_numerical_gradients": False,
+                      "surface_field": {"field": {"weight_norm": True, "geometric_init_bias": 0.4}, "use_position_encoding": True}},
+    "radiance_model": {"radiance_field": {"base_field": {"weight_norm": True}}, "use_reflection_direction": False, "use_n_dot_v": True},
+    "background_model": {"background_field": {"base_field": {"output_dim": 256, "weight_norm": True},
+                                              "head_field": {"hidden_dim": 256, "weight_norm": True}}},
+}
+
 GRID_PRESETS = ("grid", "grid_raw", "grid_unbalanced", "grid_raw_unbalanced")
+MLP_PRESETS = ("mlp", "mlp_raw")
 GRID_BG_PRESETS = ("grid_raw_grid_bg_unbalanced",)
 
 
@@ -299,6 +311,41 @@ def grid_bg_model_config() -> BaseModelConfig:
     return cfg
 
 
+def mlp_model_config() -> BaseModelConfig:
+    """ref: method_configs.py:302-356 (preset `mlp`; `mlp_raw` deep-copies it, :382-400): 8 x 256 MLPs with a skip
+    connection at layer 4 for the SDF (Softplus beta = 100, geometric init) and the radiance trunk, SDF gradients by
+    autograd (use_numerical_gradients=False), no Hessian."""
+    cfg = grid_model_config()
+    pe6 = lambda: NeRFEncodingConfig(num_frequencies=6, min_freq_exp=0.0, max_freq_exp=5, include_input=True)
+    cfg.surface_model = SurfaceModelConfig(
+        use_numerical_gradients=False,
+        surface_field=SDFFieldConfig(
+            field=MLPConfig(activation="Softplus", num_layers=8, hidden_dim=256, activation_params={"beta": 100},
+                            out_activation="None", skip_connections=(4,), geometric_init=True, weight_norm=True),
+            use_position_encoding=True, position_encoding=pe6()),
+        volume_rendering=NeuSVolumeRenderingConfig(density_fn=NeuSDensityConfig()),
+        compute_hessian=False)
+    heads = copy.deepcopy(cfg.radiance_model.modality_heads)
+    cfg.radiance_model = RadianceModelConfig(
+        radiance_field=RadianceFieldConfig(
+            base_field=MLPConfig(activation="ReLU", num_layers=8, hidden_dim=256, out_activation="ReLU", skip_connections=(4,),
+                                 weight_norm=True)),
+        radiance_feature_dim=256, modality_heads=heads, use_direction_encoding=True,
+        direction_encoding=SHEncodingConfig(degree=4), use_reflection_direction=True, use_n_dot_v=True)
+    return cfg
+
+
+def mlp_loss_config() -> LossManagerConfig:
+    """ref: method_configs.py:357-359 (the `mlp*` presets keep the eikonal loss only)"""
+    cfg = grid_loss_config()
+    cfg.geometry_losses = {"eikonal_loss": EikonalLossConfig()}
+    return cfg
+
+
+def loss_config_for(preset: str) -> LossManagerConfig:
+    return mlp_loss_config() if preset in MLP_PRESETS else grid_loss_config()
+
+
 def build_model(preset: str = "grid_raw", modalities: Optional[Dict[str, int]] = None, yaml_model: Optional[dict] = None,
                 interpolation: str = "Linear", direction_encoding: str = "nerf", log2_hashmap_size: Optional[int] = None,
                 num_samples: Optional[int] = None, num_samples_importance: Optional[int] = None,
@@ -311,6 +358,8 @@ def build_model(preset: str = "grid_raw", modalities: Optional[Dict[str, int]] =
         cfg, default_yaml = grid_model_config(), GRID_YAML_MODEL
     elif preset in GRID_BG_PRESETS:
         cfg, default_yaml = grid_bg_model_config(), GRID_BG_YAML_MODEL
+    elif preset in MLP_PRESETS:
+        cfg, default_yaml = mlp_model_config(), MLP_YAML_MODEL
     else:
         raise ValueError(f"preset '{preset}' is not on the B200 hot path")
     update_config_dict = copy.deepcopy(default_yaml if yaml_model is None else yaml_model)
@@ -321,9 +370,8 @@ def build_model(preset: str = "grid_raw", modalities: Optional[Dict[str, int]] =
     holder = _Holder()
     holder.model = cfg
     update_config(holder, {"model": update_config_dict})
-    grids = [cfg.surface_model.surface_field.field.feature_grid, cfg.radiance_model.radiance_field.base_field.feature_grid]
-    if hasattr(cfg.background_model.background_field.base_field, "feature_grid"):
-        grids.append(cfg.background_model.background_field.base_field.feature_grid)
+    grids = [f.feature_grid for f in (cfg.surface_model.surface_field.field, cfg.radiance_model.radiance_field.base_field,
+                                      cfg.background_model.background_field.base_field) if hasattr(f, "feature_grid")]
     for fg in grids:
         fg.encoding.interpolation = interpolation
         if log2_hashmap_size is not None:

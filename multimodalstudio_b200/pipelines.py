@@ -15,7 +15,7 @@ import torch
 from . import ops
 from .cameras import CameraOptimizer, CameraOptimizerConfig, Cameras, RayGenerator
 from .configs import TrainingCallbackAttributes, TrainingCallbackLocation
-from .models import MODALITY_CHANNELS, MOSAICK_PATTERNS, build_model, grid_loss_config
+from .models import MODALITY_CHANNELS, MOSAICK_PATTERNS, build_model, grid_loss_config, loss_config_for
 
 # per-modality image geometry: (width, height, focal)
 MODALITY_SENSORS = {
@@ -290,10 +290,11 @@ class RawPipeline:
 
     def __init__(self, modalities: Dict[str, int], cameras: Dict[str, Cameras], device="cuda", raw=True,
                  max_num_iterations=100000, pose_mode="SO3xR3", shared_pose=True, render_all_heads=False,
-                 process_group=None, **model_kwargs):
+                 process_group=None, preset: Optional[str] = None, **model_kwargs):
         self.device, self.raw, self.modalities = torch.device(device), raw, modalities
         self.max_num_iterations = max_num_iterations
-        self.model = build_model("grid_raw" if raw else "grid", modalities=modalities, render_all_heads=render_all_heads,
+        self.preset = preset or ("grid_raw" if raw else "grid")
+        self.model = build_model(self.preset, modalities=modalities, render_all_heads=render_all_heads,
                                  **model_kwargs).to(self.device)
         n_cam = len(next(iter(cameras.values())))
         self.camera_optimizer = CameraOptimizerConfig(mode=pose_mode, shared_optimization=shared_pose,
@@ -301,8 +302,8 @@ class RawPipeline:
                                                       ).setup(num_cameras=n_cam).to(self.device)
         self.ray_generator = RayGenerator({m: {"cameras": c.to(self.device)} for m, c in cameras.items()},
                                           self.camera_optimizer, pixel_offset=0.0)
-        self.loss_manager = grid_loss_config().setup(modalities=list(modalities), num_iterations=max_num_iterations,
-                                                     model=self.model)
+        self.loss_manager = loss_config_for(self.preset).setup(modalities=list(modalities), num_iterations=max_num_iterations,
+                                                               model=self.model)
         self.patterns = {m: torch.tensor(MOSAICK_PATTERNS[m], dtype=torch.int32, device=self.device) for m in modalities} if raw else None
         self.optimizers = {"fields": FlatAdamW(list(self.model.parameters()), lr=1e-3)}
         pose_params = list(self.camera_optimizer.parameters())

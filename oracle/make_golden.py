@@ -316,7 +316,8 @@ def golden_model(tag, level, delta, anneal, rays=10, seed_in=81, preset="grid_ra
         targets[mod] = torch.rand(rays, 1, generator=g)
         pat = torch.tensor(PATTERNS[mod])
         masks_m[mod] = pat.repeat((math.ceil(H / pat.shape[0]), math.ceil(W / pat.shape[1])))[:H, :W].type(torch.int8)
-    targets["polarization"][::4] = 1.0
+    if "polarization" in targets:
+        targets["polarization"][::4] = 1.0
     bundles = {mod: RayBundle(camera_indices=torch.zeros(rays, 1, dtype=torch.long), origins=o.clone(), directions=d.clone(),
                               up_directions=up.clone(), pixel_area=torch.ones(rays, 1), directions_norm=torch.ones(rays, 1))
                for mod, (o, d, up) in inputs.items()}
@@ -366,6 +367,12 @@ def golden_gridbg():
                  yaml_name="grid_raw_rgb_all_views_pol_10_views.yaml", modalities={"rgb": 3, "polarization": 4})
 
 
+def golden_mlp_raw():
+    """BASELINE.json configs[0]: preset mlp_raw (MLP fields, autograd SDF gradients = double backward), RGB + mono."""
+    golden_model("mlp_raw", level=16, delta=2.0 / 1024, anneal=1.0, rays=10, seed_in=281, preset="mlp_raw",
+                 yaml_name="mlp_raw.yaml", modalities={"rgb": 3, "mono": 1})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -384,3 +391,4 @@ if __name__ == "__main__":
     golden_model("late", level=16, delta=2.0 / 1024, anneal=1.0)
     golden_model("early", level=1, delta=2.0 / 16, anneal=0.0)
     golden_gridbg()
+    golden_mlp_raw()

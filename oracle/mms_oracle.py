@@ -442,6 +442,11 @@ class GridModelOracle:
 
     def sdf_field(self, x):
         """SDFField.forward (surface_field.py:99-116)"""
+        if self.cfg.get("field") == "mlp":
+            # presets `mlp*` (method_configs.py:304-335): PE -> 8 x 256 MLP, skip at layer 4, Softplus(beta=100)
+            out = mlp(self.sd, "surface_model.surface_field.field", nerf_encode(x, 6, 0.0, 5), 8, "Softplus", "None", 100.0,
+                      skips=(4,))
+            return out[..., :1], out[..., 1:]
         out = self._grid_mlp("surface_model.surface_field.field", nerf_encode(x, 6, 0.0, 5), "Softplus", "None", 100.0)
         return out[..., :1], out[..., 1:]
 
@@ -508,11 +513,20 @@ class GridModelOracle:
         starts, ends = e[:, :-1, None], e[:, 1:, None]
         s = starts.shape[1]
         pos = (oi[:, None] + di[:, None] * starts).reshape(-1, 3)
-        sdf, geo = self.sdf_field(pos)
-        delta = self.delta / np.sqrt(3)
-        sdf_t = torch.stack([self.sdf_field(pos + TAPS[i].to(pos.device) * delta)[0] for i in range(4)], 0)
-        want_h = self.training and c["compute_hessian"]
-        g, hess, normals = taps_gradients(sdf, sdf_t, delta, want_h)
+        if c.get("field") == "mlp":
+            # use_numerical_gradients=False: autograd gradient with create_graph (surface_model.py:77,193-203); no Hessian
+            if not pos.requires_grad:
+                pos.requires_grad_(True)
+            with torch.enable_grad():
+                sdf, geo = self.sdf_field(pos)
+                g = torch.autograd.grad(sdf, pos, torch.ones_like(sdf), create_graph=True, retain_graph=True)[0]
+            hess, normals = None, F.normalize(g, p=2, dim=-1)
+        else:
+            sdf, geo = self.sdf_field(pos)
+            delta = self.delta / np.sqrt(3)
+            sdf_t = torch.stack([self.sdf_field(pos + TAPS[i].to(pos.device) * delta)[0] for i in range(4)], 0)
+            want_h = self.training and c["compute_hessian"]
+            g, hess, normals = taps_gradients(sdf, sdf_t, delta, want_h)
         g3, n3 = g.view(-1, s, 3), normals.view(-1, s, 3)
         w = neus_weights(sdf.view(-1, s, 1), g3, di[:, None], ends - starts, self.inv_s(), self.anneal)
         # radiance (radiance_model.py:94-151)
@@ -531,7 +545,10 @@ class GridModelOracle:
             dir_in = 2 * (ndv * nd) + dir_in
         dir_in = nerf_encode(dir_in, 4, 0.0, 3) if c["dir_encoding"] == "nerf" else sh_encode(5, dir_in)
         rin = torch.cat([pos, dir_in, torch.cat(add, -1)], -1)
-        rfeat = self._grid_mlp("radiance_model.radiance_field.base_field", rin, "ReLU", "ReLU")
+        if c.get("field") == "mlp":
+            rfeat = mlp(sd, "radiance_model.radiance_field.base_field", rin, 8, "ReLU", "ReLU", skips=(4,))
+        else:
+            rfeat = self._grid_mlp("radiance_model.radiance_field.base_field", rin, "ReLU", "ReLU")
         for h in head_list:
             hp = f"radiance_model.modality_heads.{h}.field"
             if h == "polarization":
@@ -563,7 +580,7 @@ class GridModelOracle:
         g = torch.cat([outputs[m]["gradients"] for m in self.cfg["modalities"]], 0)
         losses["eikonal_loss"] = eikonal_loss(g)
         total = total + 0.1 * losses["eikonal_loss"]
-        if all(outputs[m]["hessians"] is not None for m in self.cfg["modalities"]):
+        if self.cfg.get("field") != "mlp" and all(outputs[m]["hessians"] is not None for m in self.cfg["modalities"]):
             h = torch.cat([outputs[m]["hessians"] for m in self.cfg["modalities"]], 0)
             losses["curvature_loss"] = curvature_loss(h)
             total = total + curvature_weight * losses["curvature_loss"]
@@ -571,10 +588,11 @@ class GridModelOracle:
 
 
 def default_cfg(modalities=None, log2_hashmap_size=19, num_samples=32, num_samples_importance=32, bg_samples=16,
-                dir_encoding="nerf", bg_grid=False):
+                dir_encoding="nerf", bg_grid=False, field="grid"):
     """confs/grid_raw.yaml over the `grid_raw` preset with the tcnn-free substitutions of SURVEY §8c."""
     return dict(modalities=modalities or {"rgb": 3, "infrared": 1, "mono": 1, "polarization": 4, "multispectral": 9},
                 log2_hashmap_size=log2_hashmap_size, num_levels=16, features_per_level=2, min_res=16, max_res=1024,
                 radius=1.0, radius_collider=1.0, num_samples=num_samples, num_samples_importance=num_samples_importance,
                 num_upsample_steps=4, bg_samples=bg_samples, base_variance=64, dir_encoding=dir_encoding,
-                use_n_dot_v=True, use_reflection_direction=False, compute_hessian=True, bg_grid=bg_grid, bg_radius=2.0)
+                use_n_dot_v=True, use_reflection_direction=False, compute_hessian=(field != "mlp"), bg_grid=bg_grid, bg_radius=2.0,
+                field=field)

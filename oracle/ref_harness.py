@@ -60,8 +60,10 @@ def build_reference_model(preset="grid_raw", yaml_name="grid_raw.yaml", modaliti
     cfgmod.Config.update_config(trainer_cfg, y)
     m = trainer_cfg.pipeline.model
     # tcnn-free substitutions
-    for fg in (m.surface_model.surface_field.field.feature_grid,
-               m.radiance_model.radiance_field.base_field.feature_grid):
+    for f in (m.surface_model.surface_field.field, m.radiance_model.radiance_field.base_field):
+        if not hasattr(f, "feature_grid"):          # presets `mlp*`: no hash grids
+            continue
+        fg = f.feature_grid
         fg.encoding.interpolation = "Linear"
         fg.encoding.implementation = "torch"
         if log2_hashmap_size is not None:
@@ -92,8 +94,9 @@ def set_schedule_state(model, level=16, delta=2.0 / 1024, anneal=1.0):
     """Hand-set what the BEFORE_TRAIN_ITERATION callbacks would set."""
     model.surface_model.volume_rendering.set_cos_anneal_ratio(anneal)
     model.surface_model.set_numerical_gradients_delta(delta)
-    model.surface_model.surface_field.field.feature_grid.update_mask(level)
-    model.radiance_model.radiance_field.base_field.feature_grid.update_mask(level)
+    for f in (model.surface_model.surface_field.field, model.radiance_model.radiance_field.base_field):
+        if hasattr(f, "feature_grid"):
+            f.feature_grid.update_mask(level)
     bgf = model.background_model.background_field.base_field
     if hasattr(bgf, "feature_grid"):
         bgf.feature_grid.update_mask(level)

@@ -30,7 +30,7 @@ def _oracle_bins(g, model, mods=None, **cfg_kw):
     return bins
 
 
-def _run_b200(g, model, render_all_heads=True, bins=None, MODS=MODS):
+def _run_b200(g, model, render_all_heads=True, bins=None, MODS=MODS, loss_cfg=None):
     from multimodalstudio_b200.cameras import RayBundle
     from multimodalstudio_b200.models import MOSAICK_PATTERNS, grid_loss_config
     model.config.render_all_heads = render_all_heads
@@ -50,10 +50,42 @@ def _run_b200(g, model, render_all_heads=True, bins=None, MODS=MODS):
     if bins is not None:
         rand["bins"] = bins
     outputs = model(bundles, rand=rand)
-    lm = grid_loss_config().setup(modalities=list(MODS), num_iterations=100000, model=model)
+    lm = (loss_cfg or grid_loss_config()).setup(modalities=list(MODS), num_iterations=100000, model=model)
     pats = {m: torch.tensor(p) for m, p in MOSAICK_PATTERNS.items()}
     losses, total = lm.compute_loss(outputs, targets, coords, int(g["step"]), mosaick_patterns=pats)
     return outputs, losses, total
+
+
+@pytest.mark.parametrize("all_heads", [True, False])
+def test_mlp_raw_preset_matches_reference(all_heads, mlp_precision):
+    """BASELINE.json configs[0] (preset mlp_raw: PE + 8 x 256 MLP fields with a skip connection, SDF gradients by
+    autograd with create_graph=True in the reference -> a double backward; here a forward-mode pass,
+    SDFField.forward_with_gradient): one training step against the fixture generated from the unmodified reference,
+    sample bins from the oracle's sampler."""
+    from multimodalstudio_b200.models import build_model, mlp_loss_config
+    g = load_golden("model_mlp_raw")
+    mods = {"rgb": 3, "mono": 1}
+    model = build_model("mlp_raw", modalities=mods, seed=int(g["seed"])).to(DEV)
+    outputs, losses, total = _run_b200(g, model, all_heads, _oracle_bins(g, model, mods, field="mlp"), MODS=mods,
+                                       loss_cfg=mlp_loss_config())
+    band = 3.0 if mlp_precision else 1.0
+    for mod in mods:
+        hit = g.t(mod + "_hit")
+        for k in (list(mods) if all_heads else [mod]) + ["accumulation", "depth", "normals"]:
+            assert_close(outputs[mod][k], g.t(f"{mod}_out_{k}"), rtol=2e-5 * band, atol=1e-6, what=f"mlp_raw {mod} {k}")
+        assert_close(outputs[mod]["gradients"][hit.to(DEV)], g.t(f"{mod}_out_gradients"), rtol=2e-5 * band, atol=1e-6, what="gradients")
+        assert outputs[mod]["hessians"] is None
+    assert "curvature_loss" not in losses
+    assert_close(total, g.t("loss_total"), rtol=2e-5 * band, what="total loss")
+    total.backward()
+    sd = dict(model.named_parameters())
+    for k in g:
+        if k.startswith("grad."):
+            gr = sd[k[5:]].grad
+            gr = gr if gr is not None else torch.zeros_like(sd[k[5:]])
+            assert_close(gr, g.t(k), rtol=2e-3 * band, atol=1e-7, what=k)
+        elif k.startswith("gradnorm."):
+            assert_close(sd[k[9:]].grad.norm(), g.t(k), rtol=2e-3 * band, what=k)
 
 
 @pytest.mark.parametrize("all_heads", [True, False])

@@ -64,4 +64,9 @@ def test_update_config_and_errors():
     with pytest.raises(ValueError):
         MLPConfig(activation="Tanh").setup(input_dim=4, output_dim=4)
     with pytest.raises(ValueError):
-        build_model("mlp_raw")
+        build_model("grid_decimated")       # per_channel_probability: not on the B200 hot path
+    mlp = build_model("mlp_raw", modalities={"rgb": 3, "mono": 1})
+    assert not mlp.surface_model.config.use_numerical_gradients and not mlp.surface_model.config.compute_hessian
+    assert [tuple(l.weight.shape) for l in mlp.surface_model.surface_field.field.layers][4] == (256, 295)   # skip at layer 4
+    bg = build_model("grid_raw_grid_bg_unbalanced", modalities={"rgb": 3, "polarization": 4}, log2_hashmap_size=8)
+    assert bg.background_model.background_field.base_field.feature_grid.radius == 2

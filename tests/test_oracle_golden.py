@@ -185,3 +185,38 @@ def test_whole_model_grid_background_preset():
             assert_close(sd[k[9:]].grad.norm(), g.t(k), rtol=5e-5, what=k)
             n_checked += 1
     assert n_checked > 60
+
+
+def test_whole_model_mlp_raw_preset():
+    """BASELINE.json configs[0]: preset mlp_raw (PE + 8 x 256 MLP fields with a skip connection, SDF gradients by
+    autograd.grad(create_graph=True) -> double backward in the reference, eikonal loss only; method_configs.py:302-400)
+    with confs/mlp_raw.yaml, RGB + mono: the host mirror's seeded parameters + the oracle reproduce the reference's step."""
+    from multimodalstudio_b200.models import MOSAICK_PATTERNS, build_model
+    g = load_golden("model_mlp_raw")
+    mods = {"rgb": 3, "mono": 1}
+    model = build_model("mlp_raw", modalities=mods, seed=int(g["seed"]))
+    assert sum(p.numel() for p in model.parameters()) == 1582101          # SURVEY 8(d)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    orc = O.GridModelOracle(sd, O.default_cfg(modalities=mods, field="mlp"))
+    orc.set_schedule_state(16, float(g["delta"]), float(g["anneal"]))
+    outputs, coords, targets = {}, {}, {}
+    for mod in mods:
+        rand = {"uniform": g.t(mod + "_rand_uniform"), "pdf": g.t(mod + "_rand_pdf"), "background": g.t(mod + "_rand_bg")}
+        outputs[mod] = orc.forward_modality(mod, g.t(mod + "_origins"), g.t(mod + "_directions"), g.t(mod + "_up"), rand)
+        coords[mod], targets[mod] = g.t(mod + "_coords"), g.t(mod + "_target")
+        for k in list(mods) + ["normals", "depth", "accumulation", "gradients"]:
+            assert_close(outputs[mod][k], g.t(f"{mod}_out_{k}"), rtol=2e-5, what=f"mlp_raw {mod} {k}")
+    losses, total = orc.loss(outputs, targets, coords, MOSAICK_PATTERNS, 0.0)
+    assert "curvature_loss" not in losses
+    assert_close(total, g.t("loss_total"), what="total loss")
+    total.backward()
+    n_checked = 0
+    for k in g:
+        if k.startswith("grad."):
+            gr = sd[k[5:]].grad if sd[k[5:]].grad is not None else torch.zeros_like(sd[k[5:]])
+            assert_close(gr, g.t(k), rtol=5e-5, atol=1e-9, what=k)
+            n_checked += 1
+        elif k.startswith("gradnorm."):
+            assert_close(sd[k[9:]].grad.norm(), g.t(k), rtol=5e-5, what=k)
+            n_checked += 1
+    assert n_checked > 60
