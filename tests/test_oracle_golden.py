@@ -171,7 +171,9 @@ def test_whole_model_grid_background_preset():
         outputs[mod] = orc.forward_modality(mod, g.t(mod + "_origins"), g.t(mod + "_directions"), g.t(mod + "_up"), rand)
         coords[mod], targets[mod] = g.t(mod + "_coords"), g.t(mod + "_target")
         for k in list(mods) + ["normals", "depth", "accumulation", "gradients", "hessians"]:
-            assert_close(outputs[mod][k], g.t(f"{mod}_out_{k}"), rtol=2e-5, what=f"gridbg {mod} {k}")
+            # finite differences with delta' = 2/1024/sqrt(3) amplify BLAS-order noise of the sdf (thread count) by 220
+            assert_close(outputs[mod][k], g.t(f"{mod}_out_{k}"), rtol=1e-4 if k in ("gradients", "hessians", "normals") else 2e-5,
+                         what=f"gridbg {mod} {k}")
     losses, total = orc.loss(outputs, targets, coords, MOSAICK_PATTERNS, float(g["loss_curvature_loss_weight"]))
     assert_close(total, g.t("loss_total"), what="total loss")
     total.backward()
