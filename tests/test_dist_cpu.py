@@ -103,6 +103,7 @@ def test_sharded_global_batch_plus_allreduce_equals_single_process():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    threads = torch.get_num_threads()
     torch.set_num_threads(2)
     sys.path.insert(0, ROOT)
     from multimodalstudio_b200.pipelines import ShardPlan
@@ -112,6 +113,7 @@ def test_sharded_global_batch_plus_allreduce_equals_single_process():
     loss1, flat1 = _flat_grad_of_plan(O, orc, params, rays, tgt, ShardPlan(COUNTS), cnt1)      # one rank, one batch
     assert abs(loss1 - loss2) < 1e-6 * max(1.0, abs(loss1)), (loss1, loss2)
     err = float((flat1 - flat2).abs().max() / flat1.abs().max())
+    torch.set_num_threads(threads)
     assert err < 1e-4, err       # equal up to fp32 reassociation (different batch shapes pick different BLAS kernels)
 
 
