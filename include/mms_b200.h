@@ -134,6 +134,11 @@ int mmsb_linear_bwd_weight(const float* dz, int64_t lddz, const float* x, int64_
 
 /* A11 on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM; csrc/mlp_tc.cu).
  * precision: 3 = "3xTF32" (hi/lo split, three TF32 MMAs per product: fp32-accurate, the parity mode),
+ *            2 = 2-term fp16 split (hi/lo fp16 operands under a per-tensor power-of-two scale, three kind::f16 MMAs per
+ *                product at twice the TF32 rate: fp32-accurate like 3xTF32).  Needs max |operand| in device memory
+ *                (`*_amax`: mmsb_amax, or the `y_amax` a producing tensor-core kernel wrote) and applies to the
+ *                CTA-pair shapes only (16-byte aligned operand rows, output width a multiple of 256, >= 18944 rows);
+ *                other shapes return MMSB_E_INVALID_ARGUMENT and are run with precision 3 by the caller,
  *            1 = single-pass TF32 (the reference's GPU runs use fp16 autocast, mlp.py:152-171 under
  *                torch.autocast; 1e-2 band).
  * Weights are consumed pre-split and pre-swizzled ("packed"): pack once per optimiser step and layer, reuse
@@ -145,10 +150,13 @@ int64_t mmsb_linear_packed_size(int32_t n_dim, int32_t k_dim, int32_t precision)
  * transpose = 1 packs B = W^T (dgrad). */
 int mmsb_linear_pack_weight(const float* w, int64_t ldw, int32_t out_dim, int32_t in_dim, int32_t transpose,
                             int32_t precision, float* packed, mmsb_stream_t stream);
-/* y = act(x W^T + b) with packed_w = pack(W, transpose = 0). */
+/* amax[0] = max(amax[0], max |x|) over a row-strided [n, cols] matrix (the caller zero-fills amax once). */
+int mmsb_amax(const float* x, int64_t ldx, int64_t n, int32_t cols, float* amax, mmsb_stream_t stream);
+/* y = act(x W^T + b) with packed_w = pack(W, transpose = 0).  x_amax: device scalar >= max |x| (precision 2 only, else
+ * NULL); y_amax (optional, any precision): device scalar updated with max(y_amax, max |y|) — zero-filled by the caller. */
 int mmsb_linear_fwd_tc(const float* x, int64_t ldx, const float* packed_w, const float* b, float* y, int64_t ldy,
                        int64_t n, int32_t in_dim, int32_t out_dim, int32_t act, float act_param, int32_t precision,
-                       mmsb_stream_t stream);
+                       const float* x_amax, float* y_amax, mmsb_stream_t stream);
 /* dx = dz W (* act_prev'(y_prev) when y_prev != NULL) with packed_wt = pack(W, transpose = 1);
  * accumulate != 0: dx += ... (a second gradient path into the same rows, e.g. the geometry-feature path of the SDF
  * network's centre rows on top of the sdf-head path that covers every row). */
@@ -171,7 +179,8 @@ int mmsb_linear_bwd_weight_tc(const float* dz, int64_t lddz, const float* x, int
  *             rank-1 term: dx = (dz W + head_d[row] * head_w[col]) * act_prev'(y_prev). */
 int mmsb_linear_fwd_head_tc(const float* x, int64_t ldx, const float* packed_w, const float* b, float* y, int64_t ldy,
                             int64_t n, int32_t in_dim, int32_t out_dim, int32_t act, float act_param, int32_t precision,
-                            const float* head_w, const float* head_b, float* head_out, mmsb_stream_t stream);
+                            const float* head_w, const float* head_b, float* head_out, const float* x_amax, float* y_amax,
+                            mmsb_stream_t stream);
 int mmsb_linear_bwd_data_head_tc(const float* y, int64_t ldy, int32_t act, float act_param, const float* head_d,
                                  const float* head_w, const float* packed_wt, float* dx, int64_t lddx, const float* y_prev,
                                  int64_t ld_yprev, int32_t act_prev, float act_prev_param, int64_t n, int32_t in_dim,

@@ -65,7 +65,7 @@ constexpr int PAIR_THREADS = (EPI_WARPS + PAIR_PROD_WARPS + 2) * 32;
 constexpr int WG_STAGE_WARPS = 16;                           // weight-gradient kernel: 2 groups of 8 staging warps
 constexpr int WG_THREADS = (WG_STAGE_WARPS + 2) * 32;        // + MMA warp + TMA loader warp
 constexpr int CH = 16;                                       // accumulator columns per epilogue chunk
-constexpr int STG_LD = 20;                                   // floats per row of the epilogue transpose buffer
+constexpr int STG_LD = 16;                                   // floats per row of the epilogue transpose buffer (chunks XOR-swizzled)
 constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
 constexpr int MAX_STAGES = 4;
 
@@ -174,6 +174,48 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int n, bool mn_major) {
 __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+// ---- precision 2: 2-term fp16 split --------------------------------------------------------------------------------
+// x (fp32) is scaled by a power of two s derived from the tensor's max |x| (s * amax in [2^14, 2^15): no fp16 overflow,
+// and every element down to amax * 2^-18 keeps a normal `lo`), then hi = fp16(s x) (11 significant bits), lo = fp16(s x -
+// hi): 22 significant bits like 3xTF32, products hi*hi + hi*lo + lo*hi as three kind::f16 MMAs (twice the TF32 rate,
+// K = 16 per instruction), and the accumulator is multiplied by the exact 1 / (s_a s_b) in the epilogue.
+__device__ __forceinline__ int f16_scale_exp(float amax) {
+  const uint32_t e = (__float_as_uint(amax) >> 23) & 0xFFu;      // biased exponent of amax >= 0
+  if (e == 0u || e == 0xFFu) return 0;                           // zero / denormal / non-finite: no scaling
+  int k = 14 + 127 - int(e);
+  return k > 120 ? 120 : (k < -120 ? -120 : k);
+}
+__device__ __forceinline__ float pow2f(int k) { return __uint_as_float(uint32_t(k + 127) << 23); }
+// two scaled fp32 values -> packed fp16x2 hi and lo (element 0 in the low half)
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  // round to 11 significant bits with one integer add and one mask (exact for fp16-normal magnitudes; below 2^-14 the
+  // conversion rounds again, an absolute error of at most 2^-25 of the scaled value, i.e. 2^-39 of the tensor's max)
+  const float ha = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xFFFFE000u);
+  const float hb = __uint_as_float((__float_as_uint(b) + 0x1000u) & 0xFFFFE000u);
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(hb), "f"(ha));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// c_format F32 (1 << 4), a/b format F16 (0), K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t make_idesc_f16(int n, int m) {
+  return (1u << 4) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+constexpr int TK16 = 64;           // fp16 elements per k-block = one 128-byte swizzle row
+
 // byte offset of 16-byte chunk c (4 fp32 along M/N) of k-row k in an MN-major SWIZZLE_128B_BASE32B tile whose 32-wide
 // panels hold TK k-rows each
 __device__ __forceinline__ uint32_t mn_offset(int c, int k) {
@@ -291,6 +333,61 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int64_t ldw, int
   }
 }
 
+// precision 2: the same tiling with fp16 hi / lo tiles of 64 k per 128-byte row (k-blocks of TK16), scaled by the power of
+// two derived from *amax (max |w|, computed by amax_kernel just before); the packed buffer ends with one float holding
+// that amax (the consuming kernels read their B scale from there).
+__host__ __device__ inline int64_t packed_floats_f16(int n, int k) {
+  return int64_t(pad16(n)) * ((k + TK16 - 1) / TK16) * 64;      // hi 128 B + lo 128 B per (row, k-block); + 4 trailer floats
+}
+__global__ void pack_weight_f16_kernel(const float* __restrict__ w, int64_t ldw, int n, int k, int transpose,
+                                       const float* __restrict__ amax, uint32_t* __restrict__ packed) {
+  const int n_pad = pad16(n), nkb = (k + TK16 - 1) / TK16;
+  const float sc = pow2f(f16_scale_exp(__ldg(amax)));
+  const int64_t total = int64_t(n_pad) * nkb * 32;       // pairs of consecutive k
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int kk = 2 * int(i % (nkb * 32)), nn = int(i / (nkb * 32));
+    float v0 = 0.f, v1 = 0.f;
+    if (nn < n) {
+      if (kk < k) v0 = transpose ? __ldg(w + int64_t(kk) * ldw + nn) : __ldg(w + int64_t(nn) * ldw + kk);
+      if (kk + 1 < k) v1 = transpose ? __ldg(w + int64_t(kk + 1) * ldw + nn) : __ldg(w + int64_t(nn) * ldw + kk + 1);
+    }
+    const int nt = nn / NT, r = nn % NT, wdt = tile_width(n_pad, nt);
+    const int kb = kk / TK16, kin = kk % TK16;
+    const int64_t base = int64_t(nt) * NT * nkb * 64 + int64_t(kb) * 2 * wdt * 32;
+    const int64_t off = int64_t(r) * 32 + (((kin >> 3) ^ (r & 7)) << 2) + ((kin & 7) >> 1);
+    uint32_t hi, lo;
+    split_f16x2(v0 * sc, v1 * sc, hi, lo);
+    packed[base + off] = hi;
+    packed[base + int64_t(wdt) * 32 + off] = lo;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<float*>(packed)[packed_floats_f16(n, k)] = __ldg(amax);
+}
+
+// out[0] = max(out[0], max |x[r, c]|) over an [n, cols] row-strided matrix (out >= 0: compared as unsigned bits)
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, int64_t ld, int64_t n, int cols,
+                                                   float* __restrict__ out) {
+  float m = 0.f;
+  const int64_t total = n * cols;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols;
+    m = fmaxf(m, fabsf(__ldg(x + r * ld + (i - r * cols))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+}
+// contiguous variant: 16-byte loads
+__global__ void __launch_bounds__(256) amax4_kernel(const float4* __restrict__ x, int64_t n4, float* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+}
+
 // ---- epilogue of one 32-row x 32-column chunk: registers -> transpose buffer -> coalesced global ------------
 enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_ATOMIC = 2 };
 
@@ -306,6 +403,15 @@ struct EpiArgs {
   // dgrad with a rank-1 term: (acc + r1_d[row] * r1_w[col]) * act'(yprev)
   const float* r1_d; const float* r1_w;
   int accumulate;                            // dgrad: C += result instead of C = result
+  // precision 2: acc_scale = 1 / (s_a s_b) is derived per tile from the operands' amax; amax_out (optional) receives
+  // max |stored value| (the scale source of the kernel that consumes C as its streamed operand)
+  const float* amax_a; const float* amax_b; float* amax_out;
+};
+// per-warp epilogue state of one tile: fused-head partial sums, accumulator scale (precision 2), running max |stored|
+struct EpiState {
+  float hacc[4];
+  float sc;
+  float amax;
 };
 
 template <int ACT>
@@ -394,14 +500,17 @@ __device__ __forceinline__ void load_colvecs(const EpiArgs& e, ColVecs& cv, int 
 
 template <int EPI, int ACT, bool RICH, typename Next>
 __device__ __forceinline__ void epilogue_rows_in(const EpiArgs& e, const float* stg, const YPrev& yp, const ColVecs& cv,
-                                                 int lane, int64_t row0, int col0, float (&hacc)[4], Next issue_next) {
+                                                 int lane, int64_t row0, int col0, EpiState& st, Next issue_next) {
+  float (&hacc)[4] = st.hacc;
   const int q4 = lane & 3, r0 = lane >> 2;
   const int col = col0 + 4 * q4;
   const float4 b4 = cv.b4, h4 = cv.h4, r4 = cv.r4;
   // rows in flight per lane (the dgrad kernels also hold two derivative operands: fewer registers left, unless the
   // kernel runs with the 128-register budget of the 14-warp pair CTAs, RICH)
   constexpr int G = (EPI == EPI_DGRAD && !RICH) ? MMSB_TC_EPI_ILP / 2 : MMSB_TC_EPI_ILP;
-  const uint32_t src = smem_u32(stg + r0 * STG_LD + 4 * q4);
+  // transpose buffer: row r holds its four 16-byte chunks at positions c ^ ((r >> 1) & 3): the row-per-lane stores of
+  // epilogue_stage and these 4-lanes-per-row loads are both free of bank conflicts (rows r0 + 8 i share the swizzle)
+  const uint32_t src = smem_u32(stg + r0 * STG_LD + 4 * (q4 ^ ((r0 >> 1) & 3)));
   float* dst = e.C ? e.C + (row0 + r0) * e.ldc + col : nullptr;
   const int64_t step = 8 * e.ldc;
 #pragma unroll
@@ -412,6 +521,10 @@ __device__ __forceinline__ void epilogue_rows_in(const EpiArgs& e, const float* 
     // the transposing stores have been consumed by now: the accumulator registers can take the next TMEM read without
     // the read-after-write stall an issue right behind the stores would see
     if (i0 == 0) issue_next();
+    if (e.amax_a != nullptr) {           // precision 2: undo the operands' power-of-two scales (exact)
+#pragma unroll
+      for (int j = 0; j < G; ++j) { x[j].x *= st.sc; x[j].y *= st.sc; x[j].z *= st.sc; x[j].w *= st.sc; }
+    }
 #pragma unroll
     for (int j = 0; j < G; ++j) {
       const int i = i0 + j;
@@ -439,6 +552,11 @@ __device__ __forceinline__ void epilogue_rows_in(const EpiArgs& e, const float* 
           x[j].x += c.x; x[j].y += c.y; x[j].z += c.z; x[j].w += c.w;
         }
       }
+      if (e.amax_out != nullptr) {
+#pragma unroll
+        for (int j = 0; j < G; ++j)
+          st.amax = fmaxf(fmaxf(st.amax, fmaxf(fabsf(x[j].x), fabsf(x[j].y))), fmaxf(fabsf(x[j].z), fabsf(x[j].w)));
+      }
 #pragma unroll
       for (int j = 0; j < G; ++j) *reinterpret_cast<float4*>(dst + (i0 + j) * step) = x[j];
     }
@@ -449,7 +567,8 @@ __device__ __forceinline__ void epilogue_rows_in(const EpiArgs& e, const float* 
 // run time (one copy per kernel: the interior path above is the one that has to be fast).
 template <int EPI>
 __device__ __forceinline__ void epilogue_rows_edge(const EpiArgs& e, const float* stg, const YPrev& yp, int lane, int64_t row0,
-                                                int col0, bool vec_ok, float (&hacc)[4], int ACT) {
+                                                int col0, bool vec_ok, EpiState& st, int ACT) {
+  float (&hacc)[4] = st.hacc;
   const int q4 = lane & 3;
   const int col = col0 + 4 * q4;
   if (col >= e.N) return;
@@ -465,7 +584,8 @@ __device__ __forceinline__ void epilogue_rows_edge(const EpiArgs& e, const float
     const int r = (lane >> 2) + 8 * i;
     const int64_t row = row0 + r;
     if (row >= e.M) continue;
-    float4 x = lds128(smem_u32(stg + r * STG_LD + 4 * q4));
+    float4 x = lds128(smem_u32(stg + r * STG_LD + 4 * (q4 ^ ((r >> 1) & 3))));
+    if (e.amax_a != nullptr) { x.x *= st.sc; x.y *= st.sc; x.z *= st.sc; x.w *= st.sc; }
     float* dst = e.C + row * e.ldc + col;
     if (EPI == EPI_FWD) {
       x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
@@ -486,6 +606,12 @@ __device__ __forceinline__ void epilogue_rows_edge(const EpiArgs& e, const float
         y.z = act_bwd_from_y(y.z, ACT, e.act_prev_param); y.w = act_bwd_from_y(y.w, ACT, e.act_prev_param);
         x.x *= y.x; x.y *= y.y; x.z *= y.z; x.w *= y.w;
       }
+    }
+    if (EPI != EPI_ATOMIC && e.amax_out != nullptr) {
+      st.amax = fmaxf(st.amax, fabsf(x.x));
+      if (col + 1 < e.N) st.amax = fmaxf(st.amax, fabsf(x.y));
+      if (col + 2 < e.N) st.amax = fmaxf(st.amax, fabsf(x.z));
+      if (col + 3 < e.N) st.amax = fmaxf(st.amax, fabsf(x.w));
     }
     if (EPI == EPI_ATOMIC) {
       const int64_t cs = e.cs ? e.cs : 1;
@@ -515,7 +641,7 @@ __device__ __forceinline__ void epilogue_rows_edge(const EpiArgs& e, const float
 __device__ __forceinline__ void epilogue_stage(const uint32_t (&v)[CH], float* stg, int lane) {
 #pragma unroll
   for (int j = 0; j < CH / 4; ++j)
-    sts128(smem_u32(stg + lane * STG_LD + 4 * j),
+    sts128(smem_u32(stg + lane * STG_LD + 4 * (j ^ ((lane >> 1) & 3))),
            make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                        __uint_as_float(v[4 * j + 3])));
 }
@@ -532,17 +658,17 @@ __device__ __forceinline__ int chunk_act(const EpiArgs& e) {
 template <int EPI, bool RICH, typename Next>
 __device__ __forceinline__ void epilogue_chunk_rows(const EpiArgs& e, float* stg, const YPrev& yp, const ColVecs& cv,
                                                     bool interior, int act, int lane, int64_t row0, int col0, bool vec_ok,
-                                                    float (&hacc)[4], Next issue_next) {
+                                                    EpiState& st, Next issue_next) {
   __syncwarp();
   if (interior) {
     switch (act) {
-      case MMSB_ACT_RELU: epilogue_rows_in<EPI, MMSB_ACT_RELU, RICH>(e, stg, yp, cv, lane, row0, col0, hacc, issue_next); break;
-      case MMSB_ACT_SOFTPLUS: epilogue_rows_in<EPI, MMSB_ACT_SOFTPLUS, RICH>(e, stg, yp, cv, lane, row0, col0, hacc, issue_next); break;
-      default: epilogue_rows_in<EPI, MMSB_ACT_NONE, RICH>(e, stg, yp, cv, lane, row0, col0, hacc, issue_next); break;
+      case MMSB_ACT_RELU: epilogue_rows_in<EPI, MMSB_ACT_RELU, RICH>(e, stg, yp, cv, lane, row0, col0, st, issue_next); break;
+      case MMSB_ACT_SOFTPLUS: epilogue_rows_in<EPI, MMSB_ACT_SOFTPLUS, RICH>(e, stg, yp, cv, lane, row0, col0, st, issue_next); break;
+      default: epilogue_rows_in<EPI, MMSB_ACT_NONE, RICH>(e, stg, yp, cv, lane, row0, col0, st, issue_next); break;
     }
   } else {
     issue_next();
-    epilogue_rows_edge<EPI>(e, stg, yp, lane, row0, col0, vec_ok, hacc, act);
+    epilogue_rows_edge<EPI>(e, stg, yp, lane, row0, col0, vec_ok, st, act);
   }
   __syncwarp();
 }
@@ -583,7 +709,8 @@ __device__ __forceinline__ void load_yfrag(const EpiArgs& e, YFrag& y, int lane,
 
 template <int EPI, int ACT>
 __device__ __forceinline__ void epilogue_chunk_frag(const EpiArgs& e, const uint32_t (&va)[8], const uint32_t (&vb)[8],
-                                                    const YFrag& y, int lane, int64_t row0, int col0, float (&hacc)[4]) {
+                                                    const YFrag& y, int lane, int64_t row0, int col0, EpiState& st) {
+  float (&hacc)[4] = st.hacc;
   const int q4 = lane & 3;
 #pragma unroll
   for (int blk = 0; blk < 2; ++blk) {
@@ -604,6 +731,7 @@ __device__ __forceinline__ void epilogue_chunk_frag(const EpiArgs& e, const uint
       const int o = 4 * blk + 2 * (i & 1);
       const int64_t row = row0 + (lane >> 2) + 8 * i;
       float x0 = __uint_as_float(v[o]), x1 = __uint_as_float(v[o + 1]);
+      if (e.amax_a != nullptr) { x0 *= st.sc; x1 *= st.sc; }
       if (EPI == EPI_FWD) {
         x0 = act_fwd(x0 + b0, ACT, e.act_param);
         x1 = act_fwd(x1 + b1, ACT, e.act_param);
@@ -617,6 +745,7 @@ __device__ __forceinline__ void epilogue_chunk_frag(const EpiArgs& e, const uint
       }
       if (e.C != nullptr && row < e.M) {
         float* dst = e.C + row * e.ldc + col;
+        if (e.amax_out != nullptr) st.amax = fmaxf(st.amax, fmaxf(fabsf(x0), two ? fabsf(x1) : 0.f));
         if (EPI == EPI_DGRAD && e.accumulate) {
           x0 += dst[0];
           if (two) x1 += dst[1];
@@ -635,13 +764,13 @@ __device__ __forceinline__ void epilogue_chunk_frag(const EpiArgs& e, const uint
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk_frag_dispatch(const EpiArgs& e, const uint32_t (&va)[8], const uint32_t (&vb)[8],
                                                              const YFrag& y, int lane, int64_t row0, int col0,
-                                                             float (&hacc)[4]) {
+                                                             EpiState& st) {
   const int act = EPI == EPI_FWD ? e.act : (e.yprev ? e.act_prev : MMSB_ACT_NONE);
   switch (act) {
-    case MMSB_ACT_RELU: epilogue_chunk_frag<EPI, MMSB_ACT_RELU>(e, va, vb, y, lane, row0, col0, hacc); break;
-    case MMSB_ACT_SOFTPLUS: epilogue_chunk_frag<EPI, MMSB_ACT_SOFTPLUS>(e, va, vb, y, lane, row0, col0, hacc); break;
-    case MMSB_ACT_SIGMOID: epilogue_chunk_frag<EPI, MMSB_ACT_SIGMOID>(e, va, vb, y, lane, row0, col0, hacc); break;
-    default: epilogue_chunk_frag<EPI, MMSB_ACT_NONE>(e, va, vb, y, lane, row0, col0, hacc); break;
+    case MMSB_ACT_RELU: epilogue_chunk_frag<EPI, MMSB_ACT_RELU>(e, va, vb, y, lane, row0, col0, st); break;
+    case MMSB_ACT_SOFTPLUS: epilogue_chunk_frag<EPI, MMSB_ACT_SOFTPLUS>(e, va, vb, y, lane, row0, col0, st); break;
+    case MMSB_ACT_SIGMOID: epilogue_chunk_frag<EPI, MMSB_ACT_SIGMOID>(e, va, vb, y, lane, row0, col0, st); break;
+    default: epilogue_chunk_frag<EPI, MMSB_ACT_NONE>(e, va, vb, y, lane, row0, col0, st); break;
   }
 }
 
@@ -655,7 +784,20 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
   const int q = warp & 3, first = warp >> 2;
   const int nch = (w + CH - 1) / CH;
   const int64_t row0 = row_base + q * 32;
-  float hacc[4] = {0.f, 0.f, 0.f, 0.f};
+  EpiState st;
+  st.hacc[0] = st.hacc[1] = st.hacc[2] = st.hacc[3] = 0.f;
+  st.sc = 1.f;
+  st.amax = 0.f;
+  if (e.amax_a != nullptr)
+    st.sc = pow2f(-f16_scale_exp(__ldg(e.amax_a))) * pow2f(-f16_scale_exp(__ldg(e.amax_b)));
+  float (&hacc)[4] = st.hacc;
+  auto amax_flush = [&]() {
+    if (EPI == EPI_ATOMIC || e.amax_out == nullptr) return;
+    float m = st.amax;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(e.amax_out), __float_as_uint(m));
+  };
   // fused head: the four lanes that share a row combine their partial dot products; one reduction per row and warp
   // (two warps per row -> two commutative additions onto the caller's zeros: order-independent)
   auto head_flush = [&]() {
@@ -689,7 +831,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
         tmem_ld_frag(tbase + uint32_t(c * CH) + (16u << 16), vb);
         tmem_ld_wait();
         if (c + STEP >= nch) release();
-        epilogue_chunk_frag_dispatch<EPI>(e, va, vb, ynone, lane, row0, col_base + c * CH, hacc);
+        epilogue_chunk_frag_dispatch<EPI>(e, va, vb, ynone, lane, row0, col_base + c * CH, st);
       }
     } else {
       // dgrad: the derivative operand of the next chunk is what is kept in flight (registers do not allow both)
@@ -703,7 +845,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
         if (cn < nch) load_yfrag<EPI>(e, ynext, lane, row0, col_base + cn * CH);
         tmem_ld_wait();
         if (cn >= nch) release();
-        epilogue_chunk_frag_dispatch<EPI>(e, va, vb, ycur, lane, row0, col_base + c * CH, hacc);
+        epilogue_chunk_frag_dispatch<EPI>(e, va, vb, ycur, lane, row0, col_base + c * CH, st);
         if (cn < nch) ycur = ynext;
       }
     }
@@ -720,6 +862,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
         }
       }
     }
+    amax_flush();
     return;
   }
 #endif
@@ -744,12 +887,13 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
     if (interior && EPI == EPI_DGRAD && !RICH) load_colvecs<EPI>(e, cv, lane, col_base + c * CH);   // (no registers to spare earlier)
     YPrev y_next;
     if (cn < nch) load_yprev<EPI>(e, y_next, lane, row0, col_base + cn * CH, vec_y);
-    epilogue_chunk_rows<EPI, RICH>(e, stg, y_cur, cv, interior, act, lane, row0, col_base + c * CH, vec_ok, hacc, [&]() {
+    epilogue_chunk_rows<EPI, RICH>(e, stg, y_cur, cv, interior, act, lane, row0, col_base + c * CH, vec_ok, st, [&]() {
       if (LD_AHEAD && cn < nch) tmem_ld16(tmem_acc + uint32_t(cn * CH) + (uint32_t(q * 32) << 16), v);
     });
     if (EPI == EPI_DGRAD && cn < nch) y_cur = y_next;
   }
   head_flush();
+  amax_flush();
 }
 
 // Converter step of one landed A k-block (TMA path): this thread's four 16-byte chunks.  All shared-memory reads are
@@ -1141,9 +1285,15 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, 
       : "memory");
 }
 
-template <int EPI>
+// KIND 0: 3xTF32 (k-blocks of 32 fp32; the landed tile is the hi operand, the converters derive lo).
+// KIND 1: 2-term fp16 split (k-blocks of 64: TWO raw fp32 boxes land in the stage's A region and are converted IN PLACE
+//         into the fp16 hi tile [0, PART) and lo tile [PART, 2 PART): a warp owns whole 8-row swizzle atoms of both boxes,
+//         reads its 2 KB into registers, __syncwarp, writes the 1 KB hi + 1 KB lo atoms over the same bytes).
+template <int EPI, int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
     tc_rows_pair_kernel(const __grid_constant__ RowsArgs g, const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b) {
+  constexpr int KB = KIND == 1 ? TK16 : TK;           // K elements per k-block
+  constexpr int KSTEP = KIND == 1 ? 16 : 8;           // K elements per MMA
   constexpr int S = PAIR_STAGES;
   constexpr int STAGE = PAIR_STAGE;
   constexpr int HB = 128 * 128;                       // bytes of one half (128 rows) of a B part
@@ -1184,7 +1334,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int last_ksteps = (g.K - (g.nkb - 1) * TK + 7) / 8;
+  const int last_ksteps = (g.K - (g.nkb - 1) * KB + KSTEP - 1) / KSTEP;
   const int64_t my_ptiles = pair < total_ptiles ? (total_ptiles - pair + npairs - 1) / npairs : 0;
 
   if (warp < EPI_WARPS) {
@@ -1243,6 +1393,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
       }
       mbar_wait(bar_raw + 8 * s, uint32_t(it / S) & 1);
       const uint32_t hi = smem_u32(smem + s * STAGE), lo = hi + PART;
+      if constexpr (KIND == 1) {
+        // lane (r = lane & 7, j = lane >> 3) of a warp's 8-row atom: raw chunks 2j, 2j+1 of both boxes -> hi / lo chunks
+        // j (k 8j..8j+7) and j + 4 (k 32+8j..); chunk positions are XOR-swizzled with the row (SWIZZLE_128B)
+        const float sa = pow2f(f16_scale_exp(__ldg(g.epi.amax_a)));
+        const int r = lane & 7, j = lane >> 3;
+        const int cw = warp - EPI_WARPS;
+#pragma unroll 1
+        for (int grp = cw; grp < TM / 8; grp += PAIR_PROD_WARPS) {
+          const uint32_t rowb = uint32_t(grp * 8 + r) * 128u;
+          const uint32_t q0 = rowb + (uint32_t((2 * j) ^ r) << 4), q1 = rowb + (uint32_t((2 * j + 1) ^ r) << 4);
+          const float4 a0 = lds128(hi + q0), a1 = lds128(hi + q1), b0 = lds128(lo + q0), b1 = lds128(lo + q1);
+          __syncwarp();
+          uint32_t h[4], l[4];
+          split_f16x2(a0.x * sa, a0.y * sa, h[0], l[0]); split_f16x2(a0.z * sa, a0.w * sa, h[1], l[1]);
+          split_f16x2(a1.x * sa, a1.y * sa, h[2], l[2]); split_f16x2(a1.z * sa, a1.w * sa, h[3], l[3]);
+          const uint32_t c0 = rowb + (uint32_t(j ^ r) << 4), c1 = rowb + (uint32_t((j + 4) ^ r) << 4);
+          sts128u(hi + c0, h[0], h[1], h[2], h[3]);
+          sts128u(lo + c0, l[0], l[1], l[2], l[3]);
+          split_f16x2(b0.x * sa, b0.y * sa, h[0], l[0]); split_f16x2(b0.z * sa, b0.w * sa, h[1], l[1]);
+          split_f16x2(b1.x * sa, b1.y * sa, h[2], l[2]); split_f16x2(b1.z * sa, b1.w * sa, h[3], l[3]);
+          sts128u(hi + c1, h[0], h[1], h[2], h[3]);
+          sts128u(lo + c1, l[0], l[1], l[2], l[3]);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(bar_full + 8 * s);
+        continue;
+      }
 #pragma unroll
       for (int h = 0; h < NCH / 4; ++h) {
         uint32_t off[4];
@@ -1278,9 +1456,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
           const uint32_t s = it % S;
           mbar_wait(bar_empty + 8 * s, ((it / S) & 1) ^ 1);
           const uint32_t a_hi = smem_u32(smem + s * STAGE), b_hi = a_hi + 2 * PART;
-          mbar_arrive_expect_tx(bar_raw + 8 * s, uint32_t(PART));
-          tma_load_2d(a_hi, &tmap_a, kb * TK, m0, bar_raw + 8 * s);
-          if (pf && pt + npairs < total_ptiles)
+          if constexpr (KIND == 1) {
+            // two raw fp32 boxes of 32 k each (columns past K are zero-filled by the copy)
+            mbar_arrive_expect_tx(bar_raw + 8 * s, uint32_t(2 * PART));
+            tma_load_2d(a_hi, &tmap_a, kb * KB, m0, bar_raw + 8 * s);
+            tma_load_2d(a_hi + PART, &tmap_a, kb * KB + TK, m0, bar_raw + 8 * s);
+          } else {
+            mbar_arrive_expect_tx(bar_raw + 8 * s, uint32_t(PART));
+            tma_load_2d(a_hi, &tmap_a, kb * TK, m0, bar_raw + 8 * s);
+          }
+          if (KIND == 0 && pf && pt + npairs < total_ptiles)
             tma_prefetch_2d(&tmap_a, kb * TK, int(((pt + npairs) / g.n_tiles) * 2 * TM + rank * TM));
           if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * s, 4u * HB);     // both CTAs' hi + lo halves
           const int row_hi = int(tile_row0 + int64_t(kb) * 2 * NT + rank * 128);
@@ -1292,7 +1477,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
   } else if (warp == EPI_WARPS + PAIR_PROD_WARPS + 1 && rank == 0) {
     // ================= MMA issuer (leader CTA) =================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(NT >> 3) << 17) | (uint32_t((2 * TM) >> 4) << 24);
+      const uint32_t idesc = KIND == 1 ? make_idesc_f16(NT, 2 * TM)
+                                       : ((1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(NT >> 3) << 17) | (uint32_t((2 * TM) >> 4) << 24));
       uint32_t it = 0, ti = 0;
       for (int64_t pt = pair; pt < total_ptiles; pt += npairs, ++ti) {
         const uint32_t acc = ti & 1;
@@ -1306,12 +1492,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
           const uint32_t a_hi = smem_u32(smem + s * STAGE), b_hi = a_hi + 2 * PART;
           const uint64_t dah = make_desc(a_hi, 16, 1024), dal = make_desc(a_hi + PART, 16, 1024);
           const uint64_t dbh = make_desc(b_hi, 16, 1024), dbl = make_desc(b_hi + HB, 16, 1024);
-          const int ksteps = (g.dbg & 8) ? 0 : (kb == g.nkb - 1 ? last_ksteps : TK / 8);
+          const int ksteps = (g.dbg & 8) ? 0 : (kb == g.nkb - 1 ? last_ksteps : KB / KSTEP);
           for (int j = 0; j < ksteps; ++j) {
-            const uint64_t adv = uint64_t(j * 2);
-            umma_tf32_pair(d, dal + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
-            umma_tf32_pair(d, dah + adv, dbl + adv, idesc, 1u);
-            umma_tf32_pair(d, dah + adv, dbh + adv, idesc, 1u);
+            const uint64_t adv = uint64_t(j * 2);       // one MMA = 32 bytes along K in both kinds
+            if constexpr (KIND == 1) {
+              umma_f16_pair(d, dal + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
+              umma_f16_pair(d, dah + adv, dbl + adv, idesc, 1u);
+              umma_f16_pair(d, dah + adv, dbh + adv, idesc, 1u);
+            } else {
+              umma_tf32_pair(d, dal + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
+              umma_tf32_pair(d, dah + adv, dbl + adv, idesc, 1u);
+              umma_tf32_pair(d, dah + adv, dbh + adv, idesc, 1u);
+            }
           }
           umma_commit_pair(bar_empty + 8 * s);
         }
@@ -1741,14 +1933,14 @@ static bool make_packed_map(const float* packed, int64_t total_rows, CUtensorMap
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int EPI>
+template <int EPI, int KIND>
 static int launch_rows_pair(const RowsArgs& g, const CUtensorMap& map_a, cudaStream_t s, const char* what) {
   CUtensorMap map_b;
   memset(&map_b, 0, sizeof(map_b));
-  const int64_t total_rows = int64_t(pad16(g.N)) * g.nkb * 2;      // hi + lo rows of every k-block
+  const int64_t total_rows = int64_t(pad16(g.N)) * g.nkb * 2;      // hi + lo rows (128 B each) of every k-block
   if (!make_packed_map(g.Bp, total_rows, &map_b)) return -1000;    // caller falls back to the single-CTA kernel
   static bool configured = false;
-  auto kern = tc_rows_pair_kernel<EPI>;
+  auto kern = tc_rows_pair_kernel<EPI, KIND>;
   const int smem = PAIR_STAGES * PAIR_STAGE + STG_BYTES + 256 + 1024;
   if (!configured) {
     int rc = set_smem(kern, smem, what);
@@ -1790,12 +1982,38 @@ static int launch_rows(const RowsArgs& g_in, cudaStream_t s, const char* what) {
     static int use_pair = -1;
     if (use_pair < 0) { const char* e = getenv("MMSB_TC_PAIR"); use_pair = e ? atoi(e) : 1; }
     if (use_pair && NPARTS == 2 && tma && n_pad % NT == 0 && g.M >= 2 * TM * (kNumSMs / 2) && !(g.dbg & 5)) {
-      const int rc = launch_rows_pair<EPI>(g, map, s, what);
+      const int rc = launch_rows_pair<EPI, 0>(g, map, s, what);
       if (rc != -1000) return rc;
     }
   }
   if (tma) return launch_rows_impl<NPARTS, EPI, true>(g, map, s, what);
   return launch_rows_impl<NPARTS, EPI, false>(g, map, s, what);
+}
+
+// precision 2 applies where the CTA-pair kernel does: TMA-fed A (16-byte aligned rows), accumulators 256 wide, enough
+// rows to fill the machine; the caller (ops.py) routes every other layer shape to the 3xTF32 kernels.
+static bool f16_rows_eligible(int64_t n, int n_dim, const float* a, int64_t lda) {
+  return pad16(n_dim) % NT == 0 && n >= 2 * TM * (kNumSMs / 2) && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (lda & 3) == 0;
+}
+template <int EPI>
+static int launch_rows_f16(const RowsArgs& g_in, cudaStream_t s, const char* what) {
+  RowsArgs g = g_in;
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  const bool elig = f16_rows_eligible(g.M, g.N, g.A, g.lda);
+  if (!elig || !make_a_map(g, &map)) {
+    set_error("%s: precision 2 (fp16 split) needs 16-byte aligned operand rows, an output width that is a multiple of 256 "
+              "and at least %d rows (rows %lld, width %d, lda %lld, base %% 16 = %d, tensor map %s)", what,
+              2 * TM * (kNumSMs / 2), (long long)g.M, g.N, (long long)g.lda, int(reinterpret_cast<uintptr_t>(g.A) & 15),
+              elig ? "could not be encoded" : "not tried");
+    return MMSB_E_INVALID_ARGUMENT;
+  }
+  const int rc = launch_rows_pair<EPI, 1>(g, map, s, what);
+  if (rc == -1000) {
+    set_error("%s: could not encode the tensor map of the packed weights", what);
+    return MMSB_E_CUDA;
+  }
+  return rc;
 }
 
 template <int NPARTS, bool TMA, bool PAIR>
@@ -1856,10 +2074,11 @@ static int launch_wgrad(const WgradArgs& g, dim3 grid, cudaStream_t s, const cha
 
 using namespace mmsb;
 
-static bool valid_precision(int p) { return p == 1 || p == 3; }
+static bool valid_precision(int p) { return p == 1 || p == 2 || p == 3; }
 
 extern "C" int64_t mmsb_linear_packed_size(int32_t n_dim, int32_t k_dim, int32_t precision) {
   if (n_dim <= 0 || k_dim <= 0 || !valid_precision(precision)) return -1;
+  if (precision == 2) return tc::packed_floats_f16(n_dim, k_dim) + 4;      // + the trailer that holds max |w|
   return tc::packed_floats(n_dim, k_dim, precision == 3 ? 2 : 1);
 }
 
@@ -1868,8 +2087,21 @@ extern "C" int mmsb_linear_pack_weight(const float* w, int64_t ldw, int32_t out_
   MMSB_REQUIRE(w && packed, "linear_pack_weight: null pointer");
   MMSB_REQUIRE(out_dim > 0 && in_dim > 0 && ldw >= in_dim, "linear_pack_weight: bad shape out=%d in=%d ldw=%lld", out_dim,
                in_dim, (long long)ldw);
-  MMSB_REQUIRE(valid_precision(precision), "linear_pack_weight: precision must be 1 (TF32) or 3 (3xTF32), got %d", precision);
+  MMSB_REQUIRE(valid_precision(precision), "linear_pack_weight: precision must be 1 (TF32), 2 (fp16 split) or 3 (3xTF32), got %d", precision);
   const int n = transpose ? in_dim : out_dim, k = transpose ? out_dim : in_dim;
+  if (precision == 2) {
+    // max |w| into the buffer's trailer (zeroed first), then the scaled hi / lo split
+    float* amax = packed + tc::packed_floats_f16(n, k);
+    cudaError_t e = cudaMemsetAsync(amax, 0, 4 * sizeof(float), as_stream(stream));
+    if (e != cudaSuccess) { set_error("linear_pack_weight: memset failed: %s", cudaGetErrorString(e)); return MMSB_E_CUDA; }
+    tc::amax_kernel<<<64, 256, 0, as_stream(stream)>>>(w, ldw, out_dim, in_dim, amax);
+    if (int rc = check_launch("linear_pack_weight(amax)")) return rc;
+    const int64_t pairs = int64_t(tc::pad16(n)) * ((k + tc::TK16 - 1) / tc::TK16) * 32;
+    const int blocks2 = int(ceil_div(pairs, 256) < 4 * kNumSMs ? ceil_div(pairs, 256) : 4 * kNumSMs);
+    tc::pack_weight_f16_kernel<<<blocks2, 256, 0, as_stream(stream)>>>(w, ldw, n, k, transpose, amax,
+                                                                        reinterpret_cast<uint32_t*>(packed));
+    return check_launch("linear_pack_weight");
+  }
   const int64_t total = int64_t(tc::pad16(n)) * ((k + tc::TK - 1) / tc::TK) * tc::TK;
   const int blocks = int(ceil_div(total, 256) < 4 * kNumSMs ? ceil_div(total, 256) : 4 * kNumSMs);
   tc::pack_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, ldw, n, k, transpose, precision == 3 ? 2 : 1, packed);
@@ -1887,7 +2119,8 @@ static int epilogue_mode() {
 // ---- internal launch helpers shared by the plain and the fused-head entry points ----------------------------------
 static int rows_fwd(const float* x, int64_t ldx, const float* packed_w, const float* b, float* y, int64_t ldy, int64_t n,
                     int in_dim, int out_dim, int act, float act_param, int precision, const float* head_w,
-                    const float* head_b, float* head_out, cudaStream_t stream, const char* what) {
+                    const float* head_b, float* head_out, cudaStream_t stream, const char* what,
+                    const float* x_amax = nullptr, float* y_amax = nullptr) {
   tc::RowsArgs g{};
   g.A = x; g.lda = ldx; g.M = n; g.K = in_dim; g.Bp = packed_w; g.N = out_dim;
   g.epi.C = y; g.epi.ldc = ldy; g.epi.M = n; g.epi.N = out_dim; g.epi.bias = b; g.epi.act = act; g.epi.act_param = act_param;
@@ -1897,6 +2130,14 @@ static int rows_fwd(const float* x, int64_t ldx, const float* packed_w, const fl
   g.total_tiles = ceil_div(n, tc::TM) * g.n_tiles;
   { const char* e = getenv("MMSB_TC_DEBUG"); g.dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("MMSB_TC_PREFETCH"); g.prefetch = e ? atoi(e) : 0; }
+  g.epi.amax_out = y_amax;
+  if (precision == 2) {
+    if (x_amax == nullptr) { set_error("%s: precision 2 needs the operand's max |x| (x_amax)", what); return MMSB_E_INVALID_ARGUMENT; }
+    g.nkb = int(ceil_div(in_dim, tc::TK16));
+    g.epi.amax_a = x_amax;
+    g.epi.amax_b = packed_w + tc::packed_floats_f16(out_dim, in_dim);
+    return tc::launch_rows_f16<tc::EPI_FWD>(g, stream, what);
+  }
   return precision == 3 ? tc::launch_rows<2, tc::EPI_FWD>(g, stream, what) : tc::launch_rows<1, tc::EPI_FWD>(g, stream, what);
 }
 
@@ -1944,28 +2185,28 @@ static int rows_wgrad(const float* dz, int64_t lddz, const float* x, int64_t ldx
 
 extern "C" int mmsb_linear_fwd_tc(const float* x, int64_t ldx, const float* packed_w, const float* b, float* y, int64_t ldy,
                                   int64_t n, int32_t in_dim, int32_t out_dim, int32_t act, float act_param, int32_t precision,
-                                  mmsb_stream_t stream) {
+                                  const float* x_amax, float* y_amax, mmsb_stream_t stream) {
   MMSB_REQUIRE(x && packed_w && y, "linear_fwd_tc: null pointer");
   MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && ldx >= in_dim && ldy >= out_dim, "linear_fwd_tc: bad shape");
   MMSB_REQUIRE(act >= MMSB_ACT_NONE && act <= MMSB_ACT_SIGMOID, "linear_fwd_tc: unknown activation %d", act);
-  MMSB_REQUIRE(valid_precision(precision), "linear_fwd_tc: precision must be 1 or 3, got %d", precision);
+  MMSB_REQUIRE(valid_precision(precision), "linear_fwd_tc: precision must be 1, 2 or 3, got %d", precision);
   if (n == 0) return MMSB_OK;
   return rows_fwd(x, ldx, packed_w, b, y, ldy, n, in_dim, out_dim, act, act_param, precision, nullptr, nullptr, nullptr,
-                  as_stream(stream), "linear_fwd_tc");
+                  as_stream(stream), "linear_fwd_tc", x_amax, y_amax);
 }
 
 extern "C" int mmsb_linear_fwd_head_tc(const float* x, int64_t ldx, const float* packed_w, const float* b, float* y,
                                        int64_t ldy, int64_t n, int32_t in_dim, int32_t out_dim, int32_t act, float act_param,
                                        int32_t precision, const float* head_w, const float* head_b, float* head_out,
-                                       mmsb_stream_t stream) {
+                                       const float* x_amax, float* y_amax, mmsb_stream_t stream) {
   MMSB_REQUIRE(x && packed_w && head_w && head_out, "linear_fwd_head_tc: null pointer");
   MMSB_REQUIRE(n >= 0 && in_dim > 0 && out_dim > 0 && out_dim <= tc::NT && ldx >= in_dim && (!y || ldy >= out_dim),
                "linear_fwd_head_tc: bad shape (the fused head needs out_dim <= 256)");
   MMSB_REQUIRE(act >= MMSB_ACT_NONE && act <= MMSB_ACT_SIGMOID, "linear_fwd_head_tc: unknown activation %d", act);
-  MMSB_REQUIRE(valid_precision(precision), "linear_fwd_head_tc: precision must be 1 or 3, got %d", precision);
+  MMSB_REQUIRE(valid_precision(precision), "linear_fwd_head_tc: precision must be 1, 2 or 3, got %d", precision);
   if (n == 0) return MMSB_OK;
   return rows_fwd(x, ldx, packed_w, b, y, ldy, n, in_dim, out_dim, act, act_param, precision, head_w, head_b, head_out,
-                  as_stream(stream), "linear_fwd_head_tc");
+                  as_stream(stream), "linear_fwd_head_tc", x_amax, y_amax);
 }
 
 extern "C" int mmsb_linear_bwd_data_tc(const float* dz, int64_t lddz, const float* packed_wt, float* dx, int64_t lddx,
@@ -2026,4 +2267,16 @@ extern "C" int mmsb_linear_bwd_weight_head_tc(const float* y, int64_t ldy, int32
   if (n == 0) return MMSB_OK;
   return rows_wgrad(y, ldy, x, ldx, dw, db, n, in_dim, out_dim, precision, head_d, head_w, act, act_param, dhead_w,
                     as_stream(stream), "linear_bwd_weight_head_tc");
+}
+
+extern "C" int mmsb_amax(const float* x, int64_t ldx, int64_t n, int32_t cols, float* amax, mmsb_stream_t stream) {
+  MMSB_REQUIRE(amax && n >= 0 && cols >= 1 && ldx >= cols, "amax: bad arguments");
+  if (n == 0) return MMSB_OK;
+  MMSB_REQUIRE(x != nullptr, "amax: NULL pointer");
+  if (ldx == cols && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && ((n * cols) & 3) == 0) {
+    tc::amax4_kernel<<<4 * kNumSMs, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), n * cols / 4, amax);
+  } else {
+    tc::amax_kernel<<<4 * kNumSMs, 256, 0, as_stream(stream)>>>(x, ldx, n, cols, amax);
+  }
+  return check_launch("amax");
 }

@@ -387,12 +387,41 @@ def pack_weight(w, transpose: bool, precision: int):
     return packed
 
 
-def linear_fwd_tc(x, packed_w, b, out_dim, act, act_param, precision, out=None):
+def amax_of(x, out=None):
+    """Device scalar max |x| of a row-strided [n, cols] fp32 matrix (mmsb_amax): the scale source of a precision-2
+    (fp16 split) product whose streamed operand was not produced by a tensor-core kernel."""
+    if out is None:
+        out = torch.zeros((1,), device=x.device, dtype=torch.float32)
+    x2 = x if x.dim() == 2 else x.reshape(-1, 1)
+    call("mmsb_amax", ptr(x2), _i64(x2.stride(0)), _i64(x2.shape[0]), _i32(x2.shape[1]), ptr(out), stream_ptr())
+    return out
+
+
+F16_MIN_ROWS = 2 * 128 * 74      # the CTA-pair kernels need enough 256-row tiles to fill the machine
+
+
+def f16_eligible(x, out_dim) -> bool:
+    """Shapes the precision-2 (fp16 split) kernels cover: see include/mms_b200.h."""
+    return (out_dim % 256 == 0 and x.shape[0] >= F16_MIN_ROWS and x.stride(1) == 1 and x.stride(0) % 4 == 0
+            and x.data_ptr() % 16 == 0)
+
+
+def layer_precision(x, out_dim) -> int:
+    """Arithmetic of one layer product under the global MLP_PRECISION: mode 2 uses the fp16 split where its kernels
+    apply and 3xTF32 elsewhere (both are fp32-accurate)."""
+    if MLP_PRECISION == 2:
+        return 2 if f16_eligible(x, out_dim) else 3
+    return MLP_PRECISION
+
+
+def linear_fwd_tc(x, packed_w, b, out_dim, act, act_param, precision, out=None, x_amax=None, y_amax=None):
     n, k = x.shape
     if out is None:
         out = torch.empty((n, out_dim), device=x.device, dtype=torch.float32)
+    if precision == 2 and x_amax is None:
+        x_amax = amax_of(x)
     call("mmsb_linear_fwd_tc", ptr(x), _i64(x.stride(0)), ptr(packed_w), ptr(b), ptr(out), _i64(out.stride(0)), _i64(n),
-         _i32(k), _i32(out_dim), _i32(act), _f32(act_param), _i32(precision), stream_ptr())
+         _i32(k), _i32(out_dim), _i32(act), _f32(act_param), _i32(precision), ptr(x_amax), ptr(y_amax), stream_ptr())
     return out
 
 
@@ -420,8 +449,8 @@ _PACK_CACHE = {}
 
 def set_mlp_precision(precision: int) -> None:
     global MLP_PRECISION
-    if precision not in (0, 1, 3):
-        raise ValueError("MLP precision must be 0 (fp32 SIMT), 1 (TF32) or 3 (3xTF32)")
+    if precision not in (0, 1, 2, 3):
+        raise ValueError("MLP precision must be 0 (fp32 SIMT), 1 (TF32), 2 (fp16 split + 3xTF32) or 3 (3xTF32)")
     MLP_PRECISION = precision
     _PACK_CACHE.clear()
 
@@ -642,7 +671,7 @@ class SdfNetFn(torch.autograd.Function):
         h1 = torch.empty((n, hid), device=dev, dtype=torch.float32) if keep_h1 else None
         call("mmsb_linear_fwd_head_tc", ptr(h0), _i64(h0.stride(0)), ptr(packed_weight(w1, False, prec)), ptr(bs[1]), ptr(h1),
              _i64(hid), _i64(n), _i32(ws[1].shape[1]), _i32(hid), _i32(act), _f32(act_param), _i32(prec), ptr(ws[2]),
-             ptr(bs[2]), ptr(sdf), stream_ptr())
+             ptr(bs[2]), ptr(sdf), None, None, stream_ptr())
         geo = None
         if n_full > 0:
             h1c = h1[0::group] if group > 1 else h1[:n_full]

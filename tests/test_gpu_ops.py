@@ -452,6 +452,29 @@ def test_tc_layer_products_vs_fp64(prec, tol, n, k, o):
     assert_close(db, dz.double().sum(0), rtol=2e-5, what="bias grad")
 
 
+@pytest.mark.parametrize("n,k,o,scale", [(20000, 256, 256, 1.0), (20000, 256, 256, 1e-7), (19000, 71, 256, 300.0), (50000, 319, 512, 1.0)])
+def test_tc_fp16_split_forward_vs_fp64(n, k, o, scale):
+    """Precision 2 (2-term fp16 split under a per-tensor power-of-two scale, three kind::f16 MMAs per product; opt-in,
+    forward products of the CTA-pair shapes): fp32-accurate like 3xTF32 over 10 orders of magnitude of operand scale,
+    columns of very different magnitude inside one operand, the fused amax of the output, and the shape guard."""
+    from multimodalstudio_b200 import ops
+    torch.manual_seed(n + k)
+    x = torch.randn(n, (k + 3) // 4 * 4, device=DEV).mul_(scale)[:, :k]
+    x[:, :8] *= 1e-3
+    w = torch.randn(o, k, device=DEV) * 0.1
+    b = torch.randn(o, device=DEV) * scale
+    pw = ops.pack_weight(w, False, 2)
+    y_amax = torch.zeros(1, device=DEV)
+    y = ops.linear_fwd_tc(x, pw, b, o, 2, 100.0 / max(scale, 1e-3), 2, y_amax=y_amax)
+    ref = torch.nn.functional.softplus(x.double() @ w.double().T + b.double(), beta=100.0 / max(scale, 1e-3), threshold=20.0)
+    assert_close(y, ref, rtol=1e-5, what="fp16-split forward")
+    assert abs(float(y_amax) - float(y.abs().max())) <= 1e-6 * float(y.abs().max())
+    assert abs(float(ops.amax_of(x)) - float(x.abs().max())) == 0.0
+    with pytest.raises(ValueError):                     # too few rows for the CTA-pair kernel: the caller must use 3xTF32
+        ops.linear_fwd_tc(x[:1000], pw, b, o, 0, 1.0, 2)
+    assert ops.layer_precision(x[:1000], o) == ops.MLP_PRECISION
+
+
 # The epilogue has an interior path (16-byte aligned C, whole 32 x 16 chunks) and an edge path (last rows / columns,
 # unaligned C, Sigmoid): every activation through both, forward and dgrad, rows that end inside a chunk.
 @pytest.mark.parametrize("act", [0, 1, 2, 3])
