@@ -402,8 +402,9 @@ F16_MIN_ROWS = 2 * 128 * 74      # the CTA-pair kernels need enough 256-row tile
 
 def f16_eligible(x, out_dim) -> bool:
     """Shapes the precision-2 (fp16 split) kernels cover: see include/mms_b200.h."""
-    return (out_dim % 256 == 0 and x.shape[0] >= F16_MIN_ROWS and x.stride(1) == 1 and x.stride(0) % 4 == 0
-            and x.data_ptr() % 16 == 0)
+    # (narrow inputs such as the 71-column first SDF layer are epilogue-bound: measured no gain, so they stay on 3xTF32)
+    return (out_dim % 256 == 0 and x.shape[1] >= 128 and x.shape[0] >= F16_MIN_ROWS and x.stride(1) == 1
+            and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0)
 
 
 def layer_precision(x, out_dim) -> int:
@@ -517,6 +518,8 @@ class MLPFn(torch.autograd.Function):
         in_dim = x.shape[-1]
         x2 = _rows(x, in_dim)
         prec = MLP_PRECISION if not skips else 0
+        bwd_prec = 3 if prec == 2 else prec
+        amax = None                  # max |h| of the running activation when a tensor-core epilogue produced it (mode 2)
         ws = [_f(params[2 * i]) for i in range(nl)]
         bs = [_f(params[2 * i + 1]) if params[2 * i + 1] is not None else None for i in range(nl)]
         if n_out_used is not None:
@@ -530,17 +533,25 @@ class MLPFn(torch.autograd.Function):
             if i in skips:
                 h = torch.cat([h, x2], -1) / math.sqrt(2)
                 acts_in[i] = h
+                amax = None
             a = hidden_act if i < nl - 1 else out_act
             if prec != 0 and _use_tc(ws[i]):
                 src = params[2 * i] if (n_out_used is None or i < nl - 1) else ws[i]
-                h = linear_fwd_tc(h, packed_weight(src, False, prec), bs[i], ws[i].shape[0], a, act_param, prec)
+                # mode 2: fp16 split for the forward products it covers (the output's amax comes out of the epilogue and
+                # scales the next layer's operand), 3xTF32 for everything else including the backward products
+                pf = layer_precision(h, ws[i].shape[0]) if prec == 2 else prec
+                y_amax = torch.zeros((1,), device=h.device) if prec == 2 and i < nl - 1 else None
+                h = linear_fwd_tc(h, packed_weight(src, False, pf), bs[i], ws[i].shape[0], a, act_param, pf,
+                                  x_amax=amax if pf == 2 else None, y_amax=y_amax)
+                amax = y_amax
                 if need_grad and (i > 0 or ctx.needs_input_grad[0]):
-                    packed_t[i] = packed_weight(src, True, prec)
+                    packed_t[i] = packed_weight(src, True, bwd_prec)
             else:
                 h = linear_fwd(h, ws[i], bs[i], a, act_param)
+                amax = None
             acts_in.append(h)
         ctx.save_for_backward(*acts_in, *ws)
-        ctx.prec = prec
+        ctx.prec = bwd_prec
         ctx.packed_t = packed_t
         ctx.cfg = (nl, hidden_act, act_param, out_act, tuple(skips), n_out_used, x.shape, in_dim,
                    [p is not None for p in params], [tuple(params[2 * i].shape) for i in range(nl)])
@@ -665,17 +676,29 @@ class SdfNetFn(torch.autograd.Function):
         g_dim = ws[2].shape[0] - 1
         need_grad = any(ctx.needs_input_grad)
         dev = x2.device
-        h0 = linear_fwd_tc(x2, packed_weight(w0, False, prec), bs[0], ws[0].shape[0], act, act_param, prec)
+        # mode 2: fp16 split for the forward products it covers (every row of one call takes the same path: centre, taps
+        # and sampler evaluations keep sharing one arithmetic), 3xTF32 for the backward products
+        mode2 = prec == 2
+        amaxes = torch.zeros((2,), device=dev, dtype=torch.float32) if mode2 else None
+        p0 = layer_precision(x2, ws[0].shape[0]) if mode2 else prec
+        h0 = linear_fwd_tc(x2, packed_weight(w0, False, p0), bs[0], ws[0].shape[0], act, act_param, p0,
+                           y_amax=amaxes[0:1] if mode2 else None)
         sdf = torch.zeros((n,), device=dev, dtype=torch.float32)
         keep_h1 = need_grad or n_full > 0
         h1 = torch.empty((n, hid), device=dev, dtype=torch.float32) if keep_h1 else None
-        call("mmsb_linear_fwd_head_tc", ptr(h0), _i64(h0.stride(0)), ptr(packed_weight(w1, False, prec)), ptr(bs[1]), ptr(h1),
-             _i64(hid), _i64(n), _i32(ws[1].shape[1]), _i32(hid), _i32(act), _f32(act_param), _i32(prec), ptr(ws[2]),
-             ptr(bs[2]), ptr(sdf), None, None, stream_ptr())
+        p1 = layer_precision(h0, hid) if mode2 else prec
+        call("mmsb_linear_fwd_head_tc", ptr(h0), _i64(h0.stride(0)), ptr(packed_weight(w1, False, p1)), ptr(bs[1]), ptr(h1),
+             _i64(hid), _i64(n), _i32(ws[1].shape[1]), _i32(hid), _i32(act), _f32(act_param), _i32(p1), ptr(ws[2]),
+             ptr(bs[2]), ptr(sdf), ptr(amaxes[0:1]) if p1 == 2 else None, ptr(amaxes[1:2]) if mode2 and keep_h1 else None,
+             stream_ptr())
         geo = None
         if n_full > 0:
             h1c = h1[0::group] if group > 1 else h1[:n_full]
-            geo = linear_fwd_tc(h1c, packed_weight(w2, False, prec, rows=(1, g_dim + 1)), bs[2][1:], g_dim, 0, 1.0, prec)
+            p2 = layer_precision(h1c, g_dim) if mode2 else prec
+            geo = linear_fwd_tc(h1c, packed_weight(w2, False, p2, rows=(1, g_dim + 1)), bs[2][1:], g_dim, 0, 1.0, p2,
+                                x_amax=amaxes[1:2] if p2 == 2 else None)
+        if mode2:
+            prec = 3
         ctx.cfg = (n, n_full, group, act, act_param, prec, in_dim, x.shape)
         if need_grad:
             ctx.save_for_backward(x2, h0, h1, *ws)

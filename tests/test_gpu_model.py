@@ -575,3 +575,36 @@ def test_whole_step_at_baseline_size_vs_oracle():
             failures.append((k, e_cuda, e_ref))
     record_error(T, f"worst parameter gradient vs fp64: CUDA ({worst[2]}; reference fp32 there: {worst[1]:.3e})", worst[0], 0.0)
     assert not failures, failures
+
+
+def test_precision2_forward_mode_matches_3xtf32():
+    """MLP precision mode 2 (opt-in: 2-term fp16 split for the forward products of the CTA-pair shapes, 3xTF32 for the
+    rest) against the default 3xTF32 mode on one training step large enough for the fp16 kernels to be used (>= 18944
+    rows per product): both are fp32-accurate, so losses and flat gradients agree to the products' 1e-5 band (times the
+    finite-difference amplification for the gradients)."""
+    from multimodalstudio_b200 import _lib, ops
+    from multimodalstudio_b200.pipelines import SyntheticScene
+    mods = {"rgb": 3, "mono": 1}
+    counts = {"rgb": 200, "mono": 200}
+    scene = SyntheticScene(mods, counts, seed=21)
+    cs, ts = scene.sample_batch()
+    cs, ts = {m: c.to(DEV) for m, c in cs.items()}, {m: t.to(DEV) for m, t in ts.items()}
+    res = {}
+    old = ops.MLP_PRECISION
+    try:
+        for prec in (3, 2):
+            ops.set_mlp_precision(prec)
+            pipe = _deterministic_pipe(mods, scene)
+            pipe.run_callbacks(60000)
+            _lib.start_kernel_timing(["mmsb_linear_fwd_tc", "mmsb_linear_fwd_head_tc"])
+            _, total = pipe.forward_backward(cs, ts, 60000)
+            torch.cuda.synchronize()
+            rec = _lib.stop_kernel_timing()
+            used = {int(a[11].value) for name, _, a in rec}          # the precision argument of every forward launch
+            res[prec] = (float(total), pipe.optimizers["fields"].grad.clone(), used)
+    finally:
+        ops.set_mlp_precision(old)
+    assert res[3][2] == {3} and res[2][2] == {2, 3}          # mode 2 really ran fp16-split forward products
+    assert abs(res[2][0] - res[3][0]) <= 2e-5 * abs(res[3][0])
+    err = float((res[2][1] - res[3][1]).abs().max() / res[3][1].abs().max())
+    assert err <= 5e-3, err
