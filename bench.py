@@ -587,6 +587,34 @@ def main():
             else:
                 dev_sampling = r
             torch.cuda.empty_cache()
+    # ---- fast mode, a side line only (never the headline): the same step with single-pass TF32 layer products (the
+    # precision class of the reference's own fp16-autocast GPU runs, engine/trainer.py:51-62; 1e-2 band, tests:
+    # test_mlp_precision_modes_agree / test_tc_layer_products_vs_fp64[1-...]), still one kernel per layer
+    fast_mode = None
+    if world == 1 and not args.no_e2e and not args.no_side and _ops.MLP_PRECISION == 3:
+        try:
+            pipe = None
+            torch.cuda.empty_cache()
+            _ops.set_mlp_precision(1)
+            pipe = RawPipeline(mods, scene.cameras, device=dev, raw=wl["raw"], render_all_heads=args.all_heads,
+                               num_samples=wl["n_c"], num_samples_importance=wl["n_i"], bg_samples=wl["bg"])
+            for i in range(3):
+                step_resident(i)
+            torch.cuda.synchronize()
+            k_ = max(2, args.steps // 2)
+            e0.record()
+            for i in range(k_):
+                step_resident(3 + i)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_f = e0.elapsed_time(e1) / k_
+            fast_mode = {"value": global_rays / (ms_f / 1e3), "unit": "rays/s", "ms_per_step": ms_f, "layers": LAYERS[1],
+                         "error_band": "1e-2 relative (single-pass TF32 products: 5e-3 measured per layer against fp64)",
+                         "note": "side line, NOT the headline: per-layer kernels become HBM-bound at this arithmetic cost"}
+        except Exception as e:
+            fast_mode = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        finally:
+            _ops.set_mlp_precision(3)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del resident
@@ -608,7 +636,7 @@ def main():
                 "vs_baseline": None, "dtype": {0: "f32", 1: "tf32", 2: "f32", 3: "f32"}[_ops.MLP_PRECISION], "data": "synthetic",
                 "config": cfg_out, "clocks": clk, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roof, "roofline_hashgrid": roof_hash, "cpu_baseline": cpu, "inference": inference,
-                "e2e_device_sampling": dev_sampling, "torch_gpu_baseline": torch_gpu, "impl": "b200"}
+                "e2e_device_sampling": dev_sampling, "fast_mode": fast_mode, "torch_gpu_baseline": torch_gpu, "impl": "b200"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
