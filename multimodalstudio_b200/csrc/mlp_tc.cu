@@ -1828,6 +1828,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
   }
 }
 
+// cudaFuncSetAttribute applies to the CURRENT device: a process that drives several GPUs must configure each one.
+// One flag per (kernel instantiation, device ordinal); set once, racing threads at worst repeat an idempotent call.
+struct PerDeviceFlag {
+  bool done[64] = {};
+  bool& operator()() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return done[dev & 63];
+  }
+};
+
 template <typename K>
 static int set_smem(K kern, int bytes, const char* what) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -1840,7 +1851,8 @@ static int set_smem(K kern, int bytes, const char* what) {
 
 template <int NPARTS, int EPI, bool TMA_A>
 static int launch_rows_impl(const RowsArgs& g, const CUtensorMap& map, cudaStream_t s, const char* what) {
-  static bool configured = false;
+  static PerDeviceFlag flags;
+  bool& configured = flags();
   auto kern = tc_rows_kernel<NPARTS, EPI, TMA_A>;
   if (!configured) {
     int rc = set_smem(kern, smem_bytes(NPARTS), what);
@@ -1939,7 +1951,8 @@ static int launch_rows_pair(const RowsArgs& g, const CUtensorMap& map_a, cudaStr
   memset(&map_b, 0, sizeof(map_b));
   const int64_t total_rows = int64_t(pad16(g.N)) * g.nkb * 2;      // hi + lo rows (128 B each) of every k-block
   if (!make_packed_map(g.Bp, total_rows, &map_b)) return -1000;    // caller falls back to the single-CTA kernel
-  static bool configured = false;
+  static PerDeviceFlag flags;
+  bool& configured = flags();
   auto kern = tc_rows_pair_kernel<EPI, KIND>;
   const int smem = PAIR_STAGES * PAIR_STAGE + STG_BYTES + 256 + 1024;
   if (!configured) {
@@ -2019,7 +2032,8 @@ static int launch_rows_f16(const RowsArgs& g_in, cudaStream_t s, const char* wha
 template <int NPARTS, bool TMA, bool PAIR>
 static int launch_wgrad_impl(const WgradArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, dim3 grid, cudaStream_t s,
                              const char* what) {
-  static bool configured = false;
+  static PerDeviceFlag flags;
+  bool& configured = flags();
   auto kern = tc_wgrad_kernel<NPARTS, TMA, PAIR>;
   if (!configured) {
     int rc = set_smem(kern, smem_bytes(NPARTS), what);
