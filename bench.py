@@ -376,11 +376,16 @@ def main():
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    prof_range = bool(os.environ.get("MMSB_PROFILER_RANGE"))      # `ncu --profile-from-start off`: capture the timed steps only
+    if prof_range:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(args.steps):
         step_resident(n_warm + i)
     e1.record()
     barrier()
+    if prof_range:
+        torch.cuda.profiler.stop()
     ms_total = e0.elapsed_time(e1)
     launches = _lib.launch_count() - l0
     if graphed:

@@ -9,7 +9,7 @@ python scripts/ncu_targets.py > $o/ncu_targets_$tag.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:"tc_rows|tc_wgrad|hashgrid" --launch-skip 7 -c 7 \
       -o $o/prof_$tag python scripts/ncu_targets.py > $o/ncu_$tag.log 2>&1
 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-side > $o/bench_for_ncu_$tag.log 2>&1 && \
-  ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 25000 -c 1000 --csv --log-file $o/launches_$tag.csv \
+  MMSB_PROFILER_RANGE=1 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $o/launches_$tag.csv \
       python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-side > $o/ncu_launches_$tag.log 2>&1
 python scripts/profile_step.py --steps 3 --out $o/kernels_$tag.txt > /dev/null 2>&1
 MMSB_BENCH_TABLE=$o/table_$tag.txt python bench.py > $o/bench_$tag.json 2> $o/bench_$tag.err
