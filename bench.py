@@ -295,6 +295,18 @@ def main():
                "l2": "inputs >> L2 (2x64 MiB tables + >20 GiB of activations per micro-batch)", "peaks": peak_src,
                "launch": "eager" if args.no_graph else "CUDA graphs (forward+backward per micro-batch | clip+AdamW)"}
 
+    # the keys below describe the workload of BOTH arms (the driver compares the two lines' `config`)
+    from multimodalstudio_b200 import ops as _ops
+    from multimodalstudio_b200.pipelines import ShardPlan
+    if args.mlp_precision is not None:
+        _ops.set_mlp_precision(args.mlp_precision)
+    LAYERS = {0: "fp32 SIMT GEMM", 1: "tcgen05 single-pass TF32 (1e-2 band; not the reported configuration)",
+              2: "tcgen05 2-term fp16 split (hi + lo, per-tensor power-of-two scaling) for the forward products of the CTA-pair shapes, 3xTF32 elsewhere; fp32 in / out",
+              3: "tcgen05 3xTF32, fp32 in / out (1e-5 band)"}
+    cfg_out["layers"] = LAYERS[_ops.MLP_PRECISION]
+    cfg_out["micro_batches_per_rank"] = len(ShardPlan(split_rays(wl["rays"] if strong else wl["weak_rays"], wl["modalities"]),
+                                                      world if strong else 1, rank if strong else 0, max_rays_per_micro=wl["micro"]))
+
     if args.impl == "reference":
         if rank != 0:
             return
@@ -311,17 +323,10 @@ def main():
 
     import torch.distributed as dist
     from multimodalstudio_b200 import _lib
-    from multimodalstudio_b200 import ops as _ops
     from multimodalstudio_b200.models import MODALITY_CHANNELS
-    from multimodalstudio_b200.pipelines import (MODALITY_SENSORS, DevicePixelSampler, RawPipeline, ShardPlan, SyntheticScene)
+    from multimodalstudio_b200.pipelines import (MODALITY_SENSORS, DevicePixelSampler, RawPipeline, SyntheticScene)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if args.mlp_precision is not None:
-        _ops.set_mlp_precision(args.mlp_precision)
-    LAYERS = {0: "fp32 SIMT GEMM", 1: "tcgen05 single-pass TF32 (1e-2 band; not the reported configuration)",
-              2: "tcgen05 2-term fp16 split (hi + lo, per-tensor power-of-two scaling), fp32 in / out",
-              3: "tcgen05 3xTF32, fp32 in / out (1e-5 band)"}
-    cfg_out["layers"] = LAYERS[_ops.MLP_PRECISION]
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
@@ -337,7 +342,6 @@ def main():
         seed = 654824 + rank                            # pixel_samplers.py:49-52: rank-offset seed
     local_counts = {m: b - a for m, (a, b) in plan.local.items()}
     local_rays = sum(local_counts.values())
-    cfg_out["micro_batches_per_rank"] = len(plan)
     scene = SyntheticScene(mods, gcounts, raw=wl["raw"], seed=seed, n_cam=n_cam)
     pipe = RawPipeline(mods, scene.cameras, device=dev, raw=wl["raw"], render_all_heads=args.all_heads,
                        num_samples=wl["n_c"], num_samples_importance=wl["n_i"], bg_samples=wl["bg"])

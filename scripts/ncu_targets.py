@@ -24,8 +24,11 @@ enc = HashEncodingConfig(num_levels=16, min_res=16, max_res=1024, log2_hashmap_s
 # ray-coherent points: 8195 rays through the unit sphere, 256 samples each, every sample followed by its 4 taps
 rays_o = torch.nn.functional.normalize(torch.randn(8195, 3, device=dev), dim=-1) * 2.5
 rays_d = torch.nn.functional.normalize(-rays_o + 0.3 * torch.randn(8195, 3, device=dev), dim=-1)
-t = torch.linspace(1.6, 3.4, 256, device=dev)
-centre = rays_o[:, None] + rays_d[:, None] * t[None, :, None]
+# samples between the ray's entry into and exit from the unit sphere (rays that miss it: a short chord at closest approach)
+b_ = (rays_o * rays_d).sum(-1, keepdim=True)
+disc = (b_ ** 2 - (rays_o.norm(dim=-1, keepdim=True) ** 2 - 1.0)).clamp_min(0.01).sqrt()
+t = (-b_ - disc) + (2 * disc) * torch.linspace(0.0, 1.0, 256, device=dev)[None]
+centre = rays_o[:, None] + rays_d[:, None] * t[:, :, None]
 offs = torch.tensor([[0, 0, 0], [1, -1, -1], [-1, -1, 1], [-1, 1, -1], [1, 1, 1]], device=dev, dtype=torch.float32) * (2.0 / 1024 / 3 ** 0.5)
 pts = (centre[:, :, None, :] + offs).reshape(-1, 3).contiguous()
 mask = torch.ones(32, device=dev)
