@@ -757,8 +757,9 @@ class Loss(nn.Module):
         self.config = config
         if self.config.loss != "L1" or reduction != "mean":
             raise ValueError("the B200 radiance loss implements L1 with mean reduction")
+        self.channel_probability = None
         if self.config.per_channel_probability is not None:
-            raise NotImplementedError("per_channel_probability (preset grid_decimated) is not on the B200 path")
+            self.channel_probability = torch.tensor(self.config.per_channel_probability)      # CPU, like the reference
         if self.config.scheduler is not None and "num_iterations" in kwargs:
             self.scheduler = self.config.scheduler.setup(num_iterations=kwargs["num_iterations"])
 
@@ -768,7 +769,35 @@ class Loss(nn.Module):
             weight *= self.scheduler.get_update_factor(step)
         return weight
 
-    def forward(self, output, target, step, pixel_coords=None, mosaick_pattern=None, **kwargs):
+    def _decimated(self, output, target, channel_draw=None):
+        """per_channel_probability (preset grid_decimated, losses.py:87-105).  The reference draws one channel index
+        per pixel with torch.multinomial and indexes `output[arange(n), indexes.view(-1, 1)]`: index shapes [n] and [n, 1]
+        BROADCAST to [n, n], so element (i, j) is pixel j at the channel drawn for pixel i, and the mean over the n x n
+        matrix is  (1/n) sum_j sum_c f_c |out[j, c] - tgt[j, c]|  with f_c = the fraction of this batch's draws that
+        picked channel c.  That is what is computed here (small [R, C] tensors: element-wise torch ops; the draw itself is
+        the reference's CPU torch.multinomial call, same generator state -> same indices).  `channel_draw`: optional
+        externally supplied indices [n] (tests)."""
+        n, c = output.shape
+        if len(self.channel_probability) != c:
+            raise ValueError(f"per_channel_probability has {len(self.channel_probability)} entries for {c} channels")
+        if channel_draw is None:
+            channel_draw = torch.multinomial(self.channel_probability, n, replacement=True)
+        freq = torch.bincount(channel_draw.reshape(-1).cpu(), minlength=c).to(torch.float32) / float(n)
+        freq = freq.to(output.device)
+        if self.saturation_threshold != float("inf"):
+            # SkipSaturationLoss.forward (losses.py:158-164) without a host sync: first saturated target by index
+            flat = target.reshape(-1)
+            idx = ops.first_saturated(target, self.saturation_threshold)[0]
+            has = idx < flat.numel()
+            value = flat[idx.clamp(max=flat.numel() - 1)]
+            output = torch.where((target > self.saturation_threshold) & has, value, output)
+        return ((output - target).abs() * freq[None, :]).sum() / float(n)
+
+    def forward(self, output, target, step, pixel_coords=None, mosaick_pattern=None, channel_draw=None, **kwargs):
+        if self.channel_probability is not None:
+            if mosaick_pattern is not None:
+                raise ValueError("per_channel_probability applies to demosaicked targets (preset grid_decimated)")
+            return self._decimated(output, target, channel_draw), self._weight(step)
         sat_index = None
         if self.saturation_threshold != float("inf"):
             sat_index = ops.first_saturated(target, self.saturation_threshold)
@@ -843,6 +872,12 @@ class LossManager:
             setattr(self, element, self.config.radiance_losses[element].setup(num_iterations=num_iterations, **kwargs))
         for element, cfg in self.config.geometry_losses.items():
             setattr(self, element, cfg.setup(num_iterations=num_iterations, **kwargs))
+
+    @property
+    def graph_capturable(self) -> bool:
+        """False when a loss draws random channels on the host every step (per_channel_probability): such a step cannot
+        be replayed from a CUDA graph."""
+        return all(getattr(getattr(self, mod), "channel_probability", None) is None for mod in self.modalities)
 
     def weights(self, step):
         """Loss weights in effect at `step` (the step-dependent scalars compute_loss multiplies in)."""

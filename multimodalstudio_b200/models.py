@@ -292,7 +292,7 @@ MLP_YAML_MODEL = {
                                               "head_field": {"hidden_dim": 256, "weight_norm": True}}},
 }
 
-GRID_PRESETS = ("grid", "grid_raw", "grid_unbalanced", "grid_raw_unbalanced")
+GRID_PRESETS = ("grid", "grid_raw", "grid_unbalanced", "grid_raw_unbalanced", "grid_decimated")
 MLP_PRESETS = ("mlp", "mlp_raw")
 GRID_BG_PRESETS = ("grid_raw_grid_bg_unbalanced",)
 
@@ -342,8 +342,19 @@ def mlp_loss_config() -> LossManagerConfig:
     return cfg
 
 
+def decimated_loss_config() -> LossManagerConfig:
+    """ref: method_configs.py:410-424 (preset `grid_decimated`: `grid` supervising one random channel per pixel)"""
+    cfg = grid_loss_config()
+    cfg.radiance_losses["rgb"].per_channel_probability = [0.25, 0.5, 0.25]
+    cfg.radiance_losses["multispectral"].per_channel_probability = [0.1111] * 9
+    cfg.radiance_losses["polarization"].per_channel_probability = [0.25, 0.25, 0.25, 0.25]
+    return cfg
+
+
 def loss_config_for(preset: str) -> LossManagerConfig:
-    return mlp_loss_config() if preset in MLP_PRESETS else grid_loss_config()
+    if preset in MLP_PRESETS:
+        return mlp_loss_config()
+    return decimated_loss_config() if preset == "grid_decimated" else grid_loss_config()
 
 
 def build_model(preset: str = "grid_raw", modalities: Optional[Dict[str, int]] = None, yaml_model: Optional[dict] = None,

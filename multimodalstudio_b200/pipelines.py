@@ -509,6 +509,10 @@ class RawPipeline:
         """forward + backward of one (micro-)batch from the graph captured for its key; `scales is None`: a whole
         step's batch (gradients overwrite the flat buffers), otherwise one shard (gradients accumulate)."""
         accumulate = scales is not None
+        if not self.loss_manager.graph_capturable:        # host-side random draws every step (preset grid_decimated)
+            dc = {m: c.to(self.device, non_blocking=True) for m, c in coords.items()}
+            dt = {m: t.to(self.device, non_blocking=True) for m, t in targets.items()}
+            return self.forward_backward(dc, dt, step, scales, count, accumulate)
         key = self._schedule_key(step, coords, targets, scales)
         g = self._graphs.get(key)
         if g is None:

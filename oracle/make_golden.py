@@ -367,6 +367,32 @@ def golden_gridbg():
                  yaml_name="grid_raw_rgb_all_views_pol_10_views.yaml", modalities={"rgb": 3, "polarization": 4})
 
 
+def golden_decimated():
+    """Preset grid_decimated (method_configs.py:410-424): the per_channel_probability losses of the reference on seeded
+    [n, C] renderings / targets, with the channel draws it made (torch.multinomial under the same seed)."""
+    import_reference()
+    from model_components.losses import LossConfig, SkipSaturationLossConfig
+    g = torch.Generator().manual_seed(171)
+    n = 48
+    out = {}
+    for mod, probs in (("rgb", [0.25, 0.5, 0.25]), ("multispectral", [0.1111] * 9), ("polarization", [0.25] * 4)):
+        c = len(probs)
+        rendered = torch.rand(n, c, generator=g).requires_grad_(True)
+        target = torch.rand(n, c, generator=g)
+        if mod == "polarization":
+            target[::5, 1] = 1.0
+        cfg = (SkipSaturationLossConfig(saturation_threshold=0.998, per_channel_probability=probs) if mod == "polarization"
+               else LossConfig(per_channel_probability=probs))
+        lf = cfg.setup(num_iterations=100)
+        torch.manual_seed(172)
+        loss, weight = lf(rendered, target, 10)
+        torch.manual_seed(172)
+        draw = torch.multinomial(torch.tensor(probs), n, replacement=True)
+        out.update({f"{mod}_rendered": rendered, f"{mod}_target": target, f"{mod}_draw": draw, f"{mod}_loss": loss,
+                    f"{mod}_drendered": torch.autograd.grad(loss, rendered)[0]})
+    save("losses_decimated", **out)
+
+
 def golden_mlp_raw():
     """BASELINE.json configs[0]: preset mlp_raw (MLP fields, autograd SDF gradients = double backward), RGB + mono."""
     golden_model("mlp_raw", level=16, delta=2.0 / 1024, anneal=1.0, rays=10, seed_in=281, preset="mlp_raw",
@@ -392,3 +418,4 @@ if __name__ == "__main__":
     golden_model("early", level=1, delta=2.0 / 16, anneal=0.0)
     golden_gridbg()
     golden_mlp_raw()
+    golden_decimated()

@@ -397,6 +397,18 @@ def l1_loss(output, target, sat_threshold=None):
     return F.l1_loss(output, target)
 
 
+def decimated_l1_loss(output, target, channel_draw, sat_threshold=None):
+    """Loss.forward with per_channel_probability (losses.py:87-105) exactly as the reference evaluates it: the index
+    shapes [n] and [n, 1] broadcast to an [n, n] gather (element (i, j) = pixel j at the channel drawn for pixel i)."""
+    if sat_threshold is not None:
+        m = target > sat_threshold
+        if m.any():
+            output = output.masked_fill(m, target[m].flatten()[0])
+    idx = channel_draw.view(-1, 1)
+    rows = torch.arange(output.shape[0])
+    return F.l1_loss(output[rows, idx.view(-1, 1)], target[rows, idx.view(-1, 1)])
+
+
 def eikonal_loss(gradients):
     n = torch.norm(gradients, 2, dim=-1)
     return F.mse_loss(n, torch.ones_like(n))

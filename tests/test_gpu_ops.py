@@ -594,6 +594,25 @@ def test_sdf_net_fused_head_vs_fp64(n, n_full, group):
         assert_close(a, r, rtol=3e-5, atol=1e-7, what=name)
 
 
+def test_decimated_losses_golden():
+    """Preset grid_decimated: LossManager's per_channel_probability losses against the reference fixture (the channel
+    draws of the reference are injected), value and gradient; and the preset builds + draws on its own."""
+    from multimodalstudio_b200.models import build_model, decimated_loss_config
+    g = load_golden("losses_decimated")
+    mods = {"rgb": 3, "multispectral": 9, "polarization": 4}
+    model = build_model("grid_decimated", modalities=mods, log2_hashmap_size=8)
+    lm = decimated_loss_config().setup(modalities=list(mods), num_iterations=100, model=model)
+    assert not lm.graph_capturable
+    for mod in mods:
+        out = g.t(mod + "_rendered", DEV).requires_grad_(True)
+        loss, weight = getattr(lm, mod)(out, g.t(mod + "_target", DEV), 10, channel_draw=g.t(mod + "_draw"))
+        assert_close(loss, g.t(mod + "_loss"), rtol=2e-6, what=mod)
+        assert_close(torch.autograd.grad(loss, out)[0], g.t(mod + "_drendered"), rtol=2e-6, atol=1e-9, what=mod + " grad")
+        torch.manual_seed(172)                         # the reference's own draw sequence
+        loss2, _ = getattr(lm, mod)(out.detach(), g.t(mod + "_target", DEV), 10)
+        assert_close(loss2, g.t(mod + "_loss"), rtol=2e-6, what=mod + " own draw")
+
+
 def test_device_pixel_sampler():
     """mmsb_sample_pixels: range, determinism in (seed, step, stream), uniformity, exact target gather."""
     ops = _ops()

@@ -64,7 +64,9 @@ def test_update_config_and_errors():
     with pytest.raises(ValueError):
         MLPConfig(activation="Tanh").setup(input_dim=4, output_dim=4)
     with pytest.raises(ValueError):
-        build_model("grid_decimated")       # per_channel_probability: not on the B200 hot path
+        build_model("no_such_preset")
+    from multimodalstudio_b200.models import loss_config_for
+    assert loss_config_for("grid_decimated").radiance_losses["rgb"].per_channel_probability == [0.25, 0.5, 0.25]
     mlp = build_model("mlp_raw", modalities={"rgb": 3, "mono": 1})
     assert not mlp.surface_model.config.use_numerical_gradients and not mlp.surface_model.config.compute_hessian
     assert [tuple(l.weight.shape) for l in mlp.surface_model.surface_field.field.layers][4] == (256, 295)   # skip at layer 4

@@ -222,3 +222,22 @@ def test_whole_model_mlp_raw_preset():
             assert_close(sd[k[9:]].grad.norm(), g.t(k), rtol=5e-4, what=k)
             n_checked += 1
     assert n_checked > 60
+
+
+def test_decimated_losses():
+    """Preset grid_decimated: the reference's per_channel_probability loss (an [n, n] broadcast gather, losses.py:87-105),
+    its restatement, and the closed form the B200 mirror computes: (1/n) sum_j sum_c f_c |out - tgt|, f_c = draw frequency."""
+    g = load_golden("losses_decimated")
+    for mod in ("rgb", "multispectral", "polarization"):
+        out, tgt, draw = g.t(mod + "_rendered").requires_grad_(True), g.t(mod + "_target"), g.t(mod + "_draw")
+        thr = 0.998 if mod == "polarization" else None
+        loss = O.decimated_l1_loss(out, tgt, draw, thr)
+        assert_close(loss, g.t(mod + "_loss"), rtol=1e-6, what=mod)
+        assert_close(torch.autograd.grad(loss, out)[0], g.t(mod + "_drendered"), rtol=1e-6, what=mod + " grad")
+        n, c = out.shape
+        freq = torch.bincount(draw, minlength=c).float() / n
+        o2 = out.detach()
+        if thr is not None and (tgt > thr).any():
+            o2 = o2.masked_fill(tgt > thr, tgt[tgt > thr].flatten()[0])
+        closed = ((o2 - tgt).abs() * freq[None]).sum() / n
+        assert_close(closed, g.t(mod + "_loss"), rtol=1e-6, what=mod + " closed form")
