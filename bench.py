@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — train rays/s (forward + backward + clip + AdamW) of the MMS-FW per-ray rendering hot path.
 
-    python bench.py --gpus N --steps K --warmup W [--workload sweep|grid_raw|grid] [--scaling strong|weak]
+    python bench.py --gpus N --steps K --warmup W [--workload sweep|grid_raw|grid|grid_bg|mlp_raw] [--scaling strong|weak]
                     [--impl reference]
 
 One "step" = one optimizer step of the hot path over one synthetic batch: pixel sampling -> ray generation -> NeuS
@@ -35,7 +35,17 @@ WORKLOADS = {
     "grid_raw": dict(modalities=FIVE, rays=8192, weak_rays=8192, micro=8192, n_c=32, n_i=32, bg=16, raw=True),
     # configs[1]: confs/grid.yaml, RGB + 1 extra modality, demosaicked, 4096 rays x 128 samples
     "grid": dict(modalities=["rgb", "infrared"], rays=4096, weak_rays=4096, micro=4096, n_c=64, n_i=64, bg=16, raw=False),
+    # configs[3]: confs/grid_raw_rgb_all_views_pol_10_views.yaml (hash-grid background preset), RGB + polarization, 16384 rays
+    "grid_bg": dict(modalities=["rgb", "polarization"], rays=16384, weak_rays=2048, micro=16384, n_c=32, n_i=32, bg=16, raw=True,
+                    preset="grid_raw_grid_bg_unbalanced", yaml="grid_raw_rgb_all_views_pol_10_views.yaml", oracle=dict(bg_grid=True)),
+    # configs[0]: confs/mlp_raw.yaml (MLP fields, analytic SDF gradients), 2 modalities, 1024 rays x 64 samples
+    "mlp_raw": dict(modalities=["rgb", "mono"], rays=1024, weak_rays=1024, micro=1024, n_c=32, n_i=32, bg=16, raw=True,
+                    preset="mlp_raw", yaml="mlp_raw.yaml", oracle=dict(field="mlp")),
 }
+
+
+def preset_of(wl):
+    return wl.get("preset") or ("grid_raw" if wl["raw"] else "grid")
 BASE_STEP = 60000       # late in the 100k-iteration schedule: all 16 levels active, delta = 2/1024, anneal = 1
 
 
@@ -104,11 +114,12 @@ def cpu_port_arm(wl, steps, warmup, rays_per_mod, device="cpu"):
     import mms_oracle as O
     from multimodalstudio_b200.models import MOSAICK_PATTERNS, build_model
     mods, scene = _synthetic_inputs(wl, rays_per_mod)
-    model = build_model("grid_raw", modalities=mods, num_samples=wl["n_c"], num_samples_importance=wl["n_i"], bg_samples=wl["bg"])
+    model = build_model(preset_of(wl), modalities=mods, num_samples=wl["n_c"], num_samples_importance=wl["n_i"], bg_samples=wl["bg"])
     dev = torch.device(device)
     sd = {k: v.detach().to(dev).requires_grad_(True) for k, v in model.state_dict().items()}
     del model
-    cfg = O.default_cfg(modalities=mods, num_samples=wl["n_c"], num_samples_importance=wl["n_i"], bg_samples=wl["bg"])
+    cfg = O.default_cfg(modalities=mods, num_samples=wl["n_c"], num_samples_importance=wl["n_i"], bg_samples=wl["bg"],
+                        **wl.get("oracle", {}))
     cams = {m: (c.camera_to_worlds.to(dev), c.intrinsics.to(dev), c.distortion_params.to(dev)) for m, c in scene.cameras.items()}
     times = []
     batches = [scene.sample_batch() for _ in range(warmup + steps)]       # drawn with the CPU generator
@@ -159,7 +170,7 @@ def cpu_reference_arm(wl, steps, warmup, rays_per_mod):
         import mms_oracle as O
         from multimodalstudio_b200.models import MOSAICK_PATTERNS
         mods, scene = _synthetic_inputs(wl, rays_per_mod)
-        model, tc = RH.build_reference_model(preset="grid_raw" if wl["raw"] else "grid", yaml_name="grid_raw.yaml" if wl["raw"] else "grid.yaml",
+        model, tc = RH.build_reference_model(preset=preset_of(wl), yaml_name=wl.get("yaml") or ("grid_raw.yaml" if wl["raw"] else "grid.yaml"),
                                              modalities=mods, num_samples=wl["n_c"], num_samples_importance=wl["n_i"], bg_samples=wl["bg"])
         RH.set_schedule_state(model, 16, 2.0 / 1024, 1.0)
         model.train()
@@ -343,7 +354,7 @@ def main():
     local_counts = {m: b - a for m, (a, b) in plan.local.items()}
     local_rays = sum(local_counts.values())
     scene = SyntheticScene(mods, gcounts, raw=wl["raw"], seed=seed, n_cam=n_cam)
-    pipe = RawPipeline(mods, scene.cameras, device=dev, raw=wl["raw"], render_all_heads=args.all_heads,
+    pipe = RawPipeline(mods, scene.cameras, device=dev, raw=wl["raw"], render_all_heads=args.all_heads, preset=preset_of(wl),
                        num_samples=wl["n_c"], num_samples_importance=wl["n_i"], bg_samples=wl["bg"])
     n_batches = 4
     resident = []
@@ -605,7 +616,7 @@ def main():
             pipe = None
             torch.cuda.empty_cache()
             _ops.set_mlp_precision(1)
-            pipe = RawPipeline(mods, scene.cameras, device=dev, raw=wl["raw"], render_all_heads=args.all_heads,
+            pipe = RawPipeline(mods, scene.cameras, device=dev, raw=wl["raw"], render_all_heads=args.all_heads, preset=preset_of(wl),
                                num_samples=wl["n_c"], num_samples_importance=wl["n_i"], bg_samples=wl["bg"])
             for i in range(3):
                 step_resident(i)

@@ -91,10 +91,10 @@ class SDFField(SurfaceField):
         n = x.shape[0]
         pe = enc(x)                                                        # [n, P]
         # tangents of the encoding: d/dx_k of [x, sin(f x_d), sin(f x_d + pi/2)] (encodings.py:161-182)
-        fr = torch.tensor(enc.freqs, device=x.device, dtype=torch.float32)  # [K]
+        fr = ops.const_tensor(("nerf_freqs", tuple(enc.freqs)), lambda: torch.tensor(enc.freqs, dtype=torch.float32), x.device)  # [K]
         k_ = fr.shape[0]
         s = x[:, :, None] * fr                                             # [n, 3, K]
-        eye = torch.eye(3, device=x.device, dtype=torch.float32)
+        eye = ops.const_tensor("eye3", lambda: torch.eye(3, dtype=torch.float32), x.device)
         d_sin = (fr * torch.cos(s))[:, None, :, :] * eye[None, :, :, None]               # [n, k, d, K]
         d_cos = (fr * torch.cos(s + math.pi / 2.0))[:, None, :, :] * eye[None, :, :, None]
         parts = ([eye[None].expand(n, 3, 3)] if enc.include_input else []) + [d_sin.reshape(n, 3, 3 * k_), d_cos.reshape(n, 3, 3 * k_)]

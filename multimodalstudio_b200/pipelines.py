@@ -489,7 +489,8 @@ class RawPipeline:
         weights = tuple(float(w) for w in self.loss_manager.weights(step))
         shapes = tuple((m, tuple(c.shape), tuple(targets[m].shape)) for m, c in coords.items())
         sc = tuple(sorted(scales.items())) if scales is not None else None
-        return (float(sm.numerical_gradients_delta), float(sm.volume_rendering._cos_anneal_ratio), levels, weights, shapes,
+        delta = sm.numerical_gradients_delta              # None for the analytic-gradient presets (`mlp*`)
+        return (float(delta) if delta is not None else 0.0, float(sm.volume_rendering._cos_anneal_ratio), levels, weights, shapes,
                 sc, ops.MLP_PRECISION)
 
     def train_step_graphed(self, step, coords, targets):

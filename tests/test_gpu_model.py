@@ -608,3 +608,35 @@ def test_precision2_forward_mode_matches_3xtf32():
     assert abs(res[2][0] - res[3][0]) <= 2e-5 * abs(res[3][0])
     err = float((res[2][1] - res[3][1]).abs().max() / res[3][1].abs().max())
     assert err <= 5e-3, err
+
+
+@pytest.mark.parametrize("preset,mods", [("mlp_raw", {"rgb": 3, "mono": 1}),
+                                         ("grid_raw_grid_bg_unbalanced", {"rgb": 3, "polarization": 4})])
+def test_pipeline_steps_of_the_other_presets(preset, mods):
+    """RawPipeline with the `mlp_raw` (configs[0]) and hash-grid-background (configs[3]) presets: the CUDA-graph step
+    equals the eager step over three optimizer steps, and the loss goes down on a repeated batch."""
+    from multimodalstudio_b200.model_components import Sampler
+    from multimodalstudio_b200.pipelines import RawPipeline, SyntheticScene
+    counts = {m: 96 for m in mods}
+    scene = SyntheticScene(mods, counts, seed=31)
+    cs, ts = scene.sample_batch()
+    cs, ts = {m: c.to(DEV) for m, c in cs.items()}, {m: t.to(DEV) for m, t in ts.items()}
+    res = []
+    for graphed in (False, True):
+        pipe = RawPipeline(mods, scene.cameras, device=DEV, raw=True, preset=preset, seed=3,
+                           **({} if preset.startswith("mlp") else {"log2_hashmap_size": 12}))
+        for m in pipe.model.modules():
+            if isinstance(m, Sampler):
+                m.train_stratified = False
+                m.config.train_stratified = False
+        totals = []
+        for i in range(4):
+            fn = pipe.train_step_graphed if graphed else pipe.train_step
+            _, total = fn(60000 + i, cs, ts)
+            totals.append(float(total.item()))
+        res.append((totals, pipe.optimizers["fields"].flat.clone()))
+    (t0, p0), (t1, p1) = res
+    for a, b in zip(t0, t1):
+        assert abs(a - b) <= 1e-4 * abs(a), (t0, t1)
+    assert t0[-1] < t0[0]                                   # four AdamW steps on the same batch reduce its loss
+    assert float((p0 - p1).abs().mean()) <= 5e-5
