@@ -517,7 +517,9 @@ class MLPFn(torch.autograd.Function):
         nl = len(params) // 2
         in_dim = x.shape[-1]
         x2 = _rows(x, in_dim)
-        prec = MLP_PRECISION if not skips else 0
+        # skip-connection networks (`mlp*` presets) run on the tensor cores too: the concatenated input of the skip layer
+        # has an odd row stride, which the register-staged operand producers take (no TMA)
+        prec = MLP_PRECISION
         bwd_prec = 3 if prec == 2 else prec
         amax = None                  # max |h| of the running activation when a tensor-core epilogue produced it (mode 2)
         ws = [_f(params[2 * i]) for i in range(nl)]
