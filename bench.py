@@ -419,17 +419,23 @@ def main():
     if not args.no_e2e:
         host = HostPixelSampler(mods, gcounts, plan.local, n_cam, wl["raw"], seed)
 
-        def step_e2e(i):
+        def run_e2e(n_steps):
+            """n_steps optimizer steps, every one of them with its own host-side pixel draw + gather, pinned host ->
+            device copy and a device -> host read of its loss.  The draw for step i + 1 is made while the GPU works on
+            step i (two pinned slots), the way a dataloader worker would; all n_steps draws are inside the timed region."""
+            losses = []
             cs, ts = host.sample()
-            _, total = run_step(i, cs, ts)
-            return float(total.item())                      # device -> host read of the step's loss
+            for i in range(n_steps):
+                _, total = run_step(i, cs, ts)              # asynchronous: H2D copies + graph replays are enqueued
+                if i + 1 < n_steps:
+                    cs, ts = host.sample()                  # next batch on the CPU, overlapped with this step on the GPU
+                losses.append(float(total.item()))          # device -> host read of the step's loss
+            return losses
 
-        for i in range(2):
-            step_e2e(i)
+        run_e2e(2)
         barrier()
         e0.record()
-        for i in range(args.steps):
-            step_e2e(i)
+        run_e2e(args.steps)
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -440,7 +446,7 @@ def main():
         h2d = sum(c.numel() * c.element_size() for c in cs0.values()) + sum(x.numel() * x.element_size() for x in ts0.values())
         e2e = {"value": global_rays / (ms_e2e / 1e3), "unit": "rays/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "input_path": "CPU torch.randint pixel draw + gather from the host frame stack (pixel_samplers.py:71-89) -> pinned -> device, per rank and step"}
+               "input_path": "CPU torch.randint pixel draw + gather from the host frame stack (pixel_samplers.py:71-89) -> pinned -> device, per rank and step; the draw of step i+1 overlaps step i on the GPU"}
         del host
 
     # ---- per-kernel durations for the roofline: one more micro-batch, eager, with CUDA events around every launch of
