@@ -193,6 +193,23 @@ int mmsb_linear_bwd_data_rank1_tc(const float* dz, int64_t lddz, const float* pa
                                   int32_t in_dim, int32_t out_dim, int32_t precision, const float* head_d,
                                   const float* head_w, mmsb_stream_t stream);
 
+/* A12, the whole forward of the SDF network (surface_field.py:99-116: x -> two hidden layers -> output 0 of the last
+ * layer; mlp.py:152-171) as ONE persistent kernel on CTA pairs: the hidden activations stay on chip between the layers
+ * (layer 0's epilogue writes fp16 hi / lo operand chunks of h0 into shared memory, layer 1's MMAs consume them).
+ *   x [n, in_dim] (16-byte aligned rows, 64 < in_dim <= 80), hidden = 256, act = ReLU or Softplus(beta = act_param);
+ *   w0 [hidden, in_dim] contiguous (its row norms bound the scale of h0), packed_w0 / packed_w1 = mmsb_linear_pack_weight
+ *   (precision 2) of W0 [hidden, in_dim] / W1 [hidden, hidden]; head_w [hidden] / head_b [1] = row 0 of the last layer;
+ *   products = 3: 2-term fp16 split, three MMAs per product (fp32-accurate, per-row power-of-two scales);
+ *   products = 1: one fp16 MMA per product (the fast mode; 1e-2 band);
+ *   sdf [n] is written (not accumulated).  h0 / h1 (NULL: not stored) receive the hidden activations for the backward
+ *   kernels; h1_group = g > 1 stores only the rows r with r % g == 0 at h1[r / g] (the centre rows of the grouped layout,
+ *   whose geometry features the caller evaluates, surface_model.py:143-146). */
+int mmsb_sdf_net_fwd_fused(const float* x, int64_t ldx, int64_t n, int32_t in_dim, int32_t hidden, const float* w0,
+                           const float* packed_w0, const float* b0, const float* packed_w1, const float* b1,
+                           const float* head_w, const float* head_b, int32_t act, float act_param, int32_t products,
+                           float* h0, int64_t ldh0, float* h1, int64_t ldh1, int32_t h1_group, float* sdf,
+                           mmsb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * A17  polarization head: Stokes vector of a sample -> intensities behind the 0 / 45 / 90 / 135 degree polarizers.
  * ref: field_components/field_heads.py:90-106, model_components/polarizer.py:39-101.

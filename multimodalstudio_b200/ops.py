@@ -750,6 +750,30 @@ class SdfNetFn(torch.autograd.Function):
         return dx, None, None, None, None, dw0, db0, dw1, db1, dw2, db2
 
 
+SDF_FUSED = int(os.environ.get("MMSB_SDF_FUSED", "1"))
+
+
+def sdf_fused_eligible(x2, w0, w1, act) -> bool:
+    """Shapes mmsb_sdf_net_fwd_fused covers (include/mms_b200.h): 64 < in_dim <= 80, hidden width 256, ReLU / Softplus,
+    16-byte aligned rows."""
+    return (SDF_FUSED != 0 and MLP_PRECISION in (1, 2, 3) and 64 < x2.shape[1] <= 80 and tuple(w1.shape) == (256, 256)
+            and w0.shape[0] == 256 and act in (ACT["relu"], ACT["softplus"]) and x2.stride(1) == 1 and x2.stride(0) % 4 == 0
+            and x2.data_ptr() % 16 == 0)
+
+
+def sdf_net_fwd_fused(x2, w0, b0, w1, b1, head_w, head_b, act, act_param, products, h0=None, h1=None, h1_group=1, sdf=None):
+    """One launch: sdf = head(act(W1 act(W0 x + b0) + b1)); h0 / h1 are stored when given (see include/mms_b200.h)."""
+    n = x2.shape[0]
+    if sdf is None:
+        sdf = torch.empty((n,), device=x2.device, dtype=torch.float32)
+    w0c = _f(w0.detach())
+    call("mmsb_sdf_net_fwd_fused", ptr(x2), _i64(x2.stride(0)), _i64(n), _i32(x2.shape[1]), _i32(w1.shape[0]), ptr(w0c),
+         ptr(packed_weight(w0, False, 2)), ptr(b0), ptr(packed_weight(w1, False, 2)), ptr(b1), ptr(head_w), ptr(head_b),
+         _i32(act), _f32(act_param), _i32(products), ptr(h0), _i64(h0.stride(0) if h0 is not None else 0), ptr(h1),
+         _i64(h1.stride(0) if h1 is not None else 0), _i32(h1_group), ptr(sdf), stream_ptr())
+    return sdf
+
+
 def sdf_net_forward(x, n_full, weights, biases, act: str, act_param: float, group: int = 1):
     return SdfNetFn.apply(x, int(n_full), int(group), ACT[act], float(act_param), weights[0], biases[0], weights[1], biases[1],
                           weights[2], biases[2])
