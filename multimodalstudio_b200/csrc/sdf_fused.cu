@@ -3,14 +3,14 @@
 // ref: src/fields/surface_field.py:99-116 (SDFField.forward), src/field_components/mlp.py:152-171 (layer loop),
 //      src/model_components/surface_model.py:143-146 (the tap / sampler evaluations keep only output 0).
 //
-// One CTA pair (tcgen05.mma.cta_group::2, M = 256 rows across two SMs) per 256-row tile, 14 warps per CTA:
+// One CTA pair (tcgen05.mma.cta_group::2, M = 256 rows across two SMs) per 256-row tile, 22 warps per CTA:
 //   loader (1 thread)      TMA: this CTA's 128 rows of x (three raw fp32 boxes of 32 columns) and its HALF (128 of the 256
 //                          output columns) of every weight k-block of W0 (2 k-blocks) and W1 (4), through a 3-stage ring;
-//   4 converter warps      one thread per row: fp32 row -> per-row power-of-two scale (from the row's 2-norm) -> fp16 hi / lo
+//   4 converter warps      two threads per row: fp32 row -> per-row power-of-two scale (from the row's 2-norm) -> fp16 hi / lo
 //                          K-major SWIZZLE_128B operand tiles, IN PLACE over the landed boxes;
 //   MMA issuer (1 thread)  layer 0 into TMEM columns [0, 256), layer 1 into [256, 512): three kind::f16 MMAs per product
 //                          (lo*hi + hi*lo + hi*hi: 22 significant bits, the fp32-accurate mode) or one (fast mode);
-//   8 epilogue warps       layer 0: tcgen05.ld -> bias / activation -> fp16 hi / lo of h0 (scaled by a per-row power of two
+//   16 epilogue warps      layer 0: tcgen05.ld -> bias / activation -> fp16 hi / lo of h0 (scaled by a per-row power of two
 //                          bounded through |z| <= |x| max|W0 row| + max b0) written straight into a K-major operand chunk
 //                          in shared memory (lane = row: no transpose), 64 columns at a time through a 2-slot ring, so the
 //                          layer-1 MMAs of a chunk run while the next chunk is produced; layer 1: bias / activation /
@@ -22,8 +22,11 @@
 namespace mmsb {
 namespace tc {
 
+constexpr int SF_EPI_WARPS = 16;                  // 4 per TMEM lane quadrant: each takes a quarter of the columns
 constexpr int SF_PROD_WARPS = 4;
-constexpr int SF_THREADS = (EPI_WARPS + SF_PROD_WARPS + 2) * 32;
+constexpr int SF_THREADS = (SF_EPI_WARPS + SF_PROD_WARPS + 2) * 32;
+constexpr int SF_STG_LD = 8;                      // floats per row of a warp's transpose buffer (32 rows x 8 columns)
+constexpr int SF_STG_BYTES = SF_EPI_WARPS * 32 * SF_STG_LD * 4;
 constexpr int SF_HB = 128 * 128;                  // one CTA's half (128 rows of N) of one part (hi or lo) of a weight k-block
 constexpr int SF_BSTAGE = 2 * SF_HB;              // hi + lo
 constexpr int SF_BSTAGES = 3;
@@ -34,9 +37,8 @@ constexpr int SF_OFF_B = 0;
 constexpr int SF_OFF_X = SF_OFF_B + SF_BSTAGES * SF_BSTAGE;
 constexpr int SF_OFF_H = SF_OFF_X + SF_XREG;
 constexpr int SF_OFF_STG = SF_OFF_H + SF_HSLOTS * SF_HSLOT;
-constexpr int SF_OFF_XN = SF_OFF_STG + STG_BYTES;            // float xnorm[2][128]
-constexpr int SF_OFF_HX = SF_OFF_XN + 2 * TM * 4;            // float head partial sums [128]
-constexpr int SF_OFF_BAR = SF_OFF_HX + TM * 4;               // 16 mbarriers + constants
+constexpr int SF_OFF_XN = SF_OFF_STG + SF_STG_BYTES;         // float xnorm[2][128]
+constexpr int SF_OFF_BAR = SF_OFF_XN + 2 * TM * 4;           // 17 mbarriers + constants
 constexpr int SF_SMEM = SF_OFF_BAR + 256 + 1024 /*alignment*/;
 static_assert(SF_SMEM <= 232448, "shared memory of the fused SDF kernel");
 
@@ -47,49 +49,104 @@ struct SdfFusedArgs {
   float act_param;
   float* h0; int64_t ldh0;
   float* h1; int64_t ldh1; int h1_group;
+  int tma_store;
   float* sdf;
 };
 
+// Softplus(beta) = max(z, 0) + ln 2 / beta * lg2(1 + ex2(-beta log2(e) |z|)) with the two constants hoisted (c1, c2): six
+// instructions per element, two of them on the MUFU pipe; ReLU: one
 template <int ACT>
-__device__ __forceinline__ float sf_act(float z, float p) {
-  return act_fwd(z, ACT, p);
+__device__ __forceinline__ float sf_act(float z, float c1, float c2) {
+  if (ACT == MMSB_ACT_SOFTPLUS) return fmaf(fast_lg2(1.f + fast_ex2(fabsf(z) * c1)), c2, fmaxf(z, 0.f));
+  return fmaxf(z, 0.f);
 }
 
-// 16 post-activation values of this lane's row (columns col0..col0+15) -> transpose buffer -> coalesced 64-byte row
-// segments of C; group > 1: only rows that are multiples of `group` are kept, at row index / group
-__device__ __forceinline__ void sf_store16(float* C, int64_t ld, int64_t M, int group, int64_t grow0, int col0, const float* h,
-                                           float* stg, int lane) {
+// per-column vectors (biases, head weights): 3 KB that every epilogue warp re-reads every tile; keep them in L1 while the
+// activation stores stream through it
+__device__ __forceinline__ float4 ldg_keep(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// 8 post-activation values of this lane's row (columns col0..col0+7) -> the warp's transpose buffer -> 32-byte row segments
+// of C (16 rows per store instruction); group > 1: only rows that are multiples of `group` are kept, at row index / group
+__device__ __forceinline__ void sf_store8(float* C, int64_t ld, int64_t M, int group, int64_t grow0, int col0, const float* h,
+                                          float* stg, int lane) {
   __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    sts128(smem_u32(stg + lane * STG_LD + 4 * (j ^ ((lane >> 1) & 3))), make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
+  const int sw = (lane >> 2) & 1;
+  sts128(smem_u32(stg + lane * SF_STG_LD + 4 * (0 ^ sw)), make_float4(h[0], h[1], h[2], h[3]));
+  sts128(smem_u32(stg + lane * SF_STG_LD + 4 * (1 ^ sw)), make_float4(h[4], h[5], h[6], h[7]));
   __syncwarp();
-  const int q4 = lane & 3, r0 = lane >> 2;
+  const int jj = lane & 1;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = r0 + 8 * i;
-    const float4 v = lds128(smem_u32(stg + r * STG_LD + 4 * (q4 ^ ((r >> 1) & 3))));
+  for (int i = 0; i < 2; ++i) {
+    const int r = (lane >> 1) + 16 * i;
+    const float4 v = lds128(smem_u32(stg + r * SF_STG_LD + 4 * (jj ^ ((r >> 2) & 1))));
     int64_t row = grow0 + r;
     if (row >= M) continue;
     if (group > 1) {
       if (row % group) continue;
       row /= group;
     }
-    *reinterpret_cast<float4*>(C + row * ld + col0 + 4 * q4) = v;
+    stg_stream(C + row * ld + col0 + 4 * jj, v);
+  }
+}
+
+// The same 32 x 8 block through the TMA: the lanes write their rows into the warp's (unswizzled) buffer and one lane
+// issues a tensor-map store (rows past the end of the tensor are clipped by the copy).  No LDS / STG instruction and no
+// L1 traffic; the buffer is reused once the previous copy has READ it.
+template <int PENDING>
+__device__ __forceinline__ void sf_store8_tma(const CUtensorMap* map, int grow0, int col0, const float* h, float* stg, int lane) {
+  if (PENDING >= 0) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING >= 0 ? PENDING : 0) : "memory");
+    __syncwarp();
+  }
+  const uint32_t dst = smem_u32(stg + lane * SF_STG_LD);
+  sts128(dst, make_float4(h[0], h[1], h[2], h[3]));
+  sts128(dst + 16, make_float4(h[4], h[5], h[6], h[7]));
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(col0), "r"(grow0),
+                 "r"(smem_u32(stg))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+
+// 32 rows x 16 columns (64-byte rows, one 2 KB box): half as many rows for the copy engine as two 8-column blocks
+__device__ __forceinline__ void sf_store16_tma(const CUtensorMap* map, int grow0, int col0, const float* h, float* stg, int lane) {
+  const uint32_t dst = smem_u32(stg + lane * 16);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int jj = (j + (lane >> 1)) & 3;            // rotate the chunk order: the lanes of a quarter-warp hit distinct banks
+    sts128(dst + 16 * jj, make_float4(h[4 * jj], h[4 * jj + 1], h[4 * jj + 2], h[4 * jj + 3]));
+  }
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(col0), "r"(grow0),
+                 "r"(smem_u32(stg))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
 }
 
 template <int ACT, int NPROD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SF_THREADS, 1)
     sdf_fused_fwd_kernel(const __grid_constant__ SdfFusedArgs g, const __grid_constant__ CUtensorMap tmap_x,
-                         const __grid_constant__ CUtensorMap tmap_w0, const __grid_constant__ CUtensorMap tmap_w1) {
+                         const __grid_constant__ CUtensorMap tmap_w0, const __grid_constant__ CUtensorMap tmap_w1,
+                         const __grid_constant__ CUtensorMap tmap_h0, const __grid_constant__ CUtensorMap tmap_h1) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sb = smem_u32(smem);
   const uint32_t BR = sb + SF_OFF_B, XR = sb + SF_OFF_X, HR = sb + SF_OFF_H;
   float* stg_all = reinterpret_cast<float*>(smem + SF_OFF_STG);
   float* xnorm = reinterpret_cast<float*>(smem + SF_OFF_XN);
-  float* hx = reinterpret_cast<float*>(smem + SF_OFF_HX);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SF_OFF_BAR);
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t b_full = bar0, b_empty = bar0 + 24, x_raw = bar0 + 48, x_full = bar0 + 56, x_empty = bar0 + 64;
@@ -113,13 +170,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SF_THREADS, 1)
     mbar_init(x_full, 2 * SF_PROD_WARPS);
     mbar_init(x_empty, 1);
     mbar_init(a0_full, 1);
-    mbar_init(a0_empty, 2 * EPI_WARPS);
+    mbar_init(a0_empty, 2 * SF_EPI_WARPS);
     for (int s = 0; s < SF_HSLOTS; ++s) {
-      mbar_init(h_full + 8 * s, 2 * EPI_WARPS);
+      mbar_init(h_full + 8 * s, 2 * SF_EPI_WARPS);
       mbar_init(h_empty + 8 * s, 1);
     }
     mbar_init(a1_full, 1);
-    mbar_init(a1_empty, 2 * EPI_WARPS);
+    mbar_init(a1_empty, 2 * SF_EPI_WARPS);
     consts[0] = 0.f;
     consts[1] = 0.f;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -130,10 +187,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SF_THREADS, 1)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  if (warp < EPI_WARPS) {
+  if (warp < SF_EPI_WARPS) {
     // bound of the layer-0 pre-activations: |z[r, c]| <= |x_r|_2 * max_c |W0[c, :]|_2 + max_c b0[c]
     float wn = 0.f, bm = 0.f;
-    for (int c = t; c < NT; c += EPI_WARPS * 32) {
+    for (int c = t; c < NT; c += SF_EPI_WARPS * 32) {
       float s = 0.f;
       for (int k = 0; k < g.K0; ++k) { const float w = __ldg(g.w0 + int64_t(c) * g.K0 + k); s = fmaf(w, w, s); }
       wn = fmaxf(wn, sqrtf(s));
@@ -155,19 +212,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SF_THREADS, 1)
   const uint32_t tmem = *tmem_slot;
   const float wn_max = consts[0], b_max = consts[1];
 
-  if (warp < EPI_WARPS) {
-    // ================= epilogues (this CTA's 128 rows) =================
-    const int q = warp & 3, hf = warp >> 2;
+  if (warp < SF_EPI_WARPS) {
+    // ================= epilogues (this CTA's 128 rows; warp = row quadrant q x column quarter `part`) =================
+    const int q = warp & 3, part = warp >> 2;
     const int row = q * 32 + lane;
-    float* stg = stg_all + warp * 32 * STG_LD;
+    float* stg = stg_all + warp * 32 * SF_STG_LD;
     const int ew0 = f16_scale_exp(__ldg(g.amax_w0)), ew1 = f16_scale_exp(__ldg(g.amax_w1));
     const float p = g.act_param;
+    const float c1 = -p * 1.4426950408889634f, c2 = 0.6931471805599453f / p;
     const float head_b = g.head_b ? __ldg(g.head_b) : 0.f;
     const uint32_t lane_base = uint32_t(q * 32) << 16;
     uint32_t ti = 0;
     for (int64_t pt = pair; pt < ptiles; pt += npairs, ++ti) {
       const int64_t m0 = pt * 2 * TM + rank * TM;
-      mbar_wait(a0_full, ti & 1);
+      mbar_wait_backoff<64>(a0_full, ti & 1);
       tc_fence_after();
       // per-row scales: x was scaled by 2^ex (converters), h0 is scaled by 2^eh with one bit of headroom under the bound
       const float xn = xnorm[(ti & 1) * TM + row];
@@ -176,37 +234,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SF_THREADS, 1)
       if (ACT == MMSB_ACT_SOFTPLUS) hb += 0.6931472f / p;
       const int eh = f16_scale_exp(hb) - 1;
       const float dsc0 = pow2f(-ex) * pow2f(-ew0), sh = pow2f(eh), dsc1 = pow2f(-eh) * pow2f(-ew1);
-      // ---- layer 0: 4 chunks of 64 columns, this warp's 32-column half of each ----
+      // ---- layer 0: 4 chunks of 64 columns, this warp's 16 columns of each ----
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const uint32_t slot = c & 1, use = 2 * ti + (c >> 1);
-        const int col0 = 64 * c + 32 * hf;
-        uint32_t v[32];
-        tmem_ld16(tmem + lane_base + uint32_t(col0), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        tmem_ld16(tmem + lane_base + uint32_t(col0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        const int col0 = 64 * c + 16 * part;
+        uint32_t v[16];
+        tmem_ld16(tmem + lane_base + uint32_t(col0), v);
         tmem_ld_wait();
         if (c == 3) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(a0_empty);
         }
-        float h[32];
+        float h[16];
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 b4 = g.b0 ? __ldg(reinterpret_cast<const float4*>(g.b0 + col0) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          h[4 * j4 + 0] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 0]), dsc0, b4.x), p);
-          h[4 * j4 + 1] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 1]), dsc0, b4.y), p);
-          h[4 * j4 + 2] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 2]), dsc0, b4.z), p);
-          h[4 * j4 + 3] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 3]), dsc0, b4.w), p);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b4 = g.b0 ? ldg_keep(g.b0 + col0 + 4 * j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          h[4 * j4 + 0] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 0]), dsc0, b4.x), c1, c2);
+          h[4 * j4 + 1] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 1]), dsc0, b4.y), c1, c2);
+          h[4 * j4 + 2] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 2]), dsc0, b4.z), c1, c2);
+          h[4 * j4 + 3] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 3]), dsc0, b4.w), c1, c2);
         }
-        mbar_wait(h_empty + 8 * slot, (use & 1) ^ 1);
+        mbar_wait_backoff<64>(h_empty + 8 * slot, (use & 1) ^ 1);
         const uint32_t hi_base = HR + slot * SF_HSLOT + uint32_t(row) * 128u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
           uint32_t hh[4], ll[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) split_f16x2(h[8 * i + 2 * k] * sh, h[8 * i + 2 * k + 1] * sh, hh[k], ll[k]);
-          const uint32_t phys = uint32_t((4 * hf + i) ^ (row & 7)) << 4;
+          for (int k = 0; k < 4; ++k) split_f16x2_bounded(h[8 * i + 2 * k] * sh, h[8 * i + 2 * k + 1] * sh, hh[k], ll[k]);
+          const uint32_t phys = uint32_t((2 * part + i) ^ (row & 7)) << 4;
           sts128u(hi_base + phys, hh[0], hh[1], hh[2], hh[3]);
           if (NPROD == 3) sts128u(hi_base + PART + phys, ll[0], ll[1], ll[2], ll[3]);
         }
@@ -214,21 +271,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SF_THREADS, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(h_full + 8 * slot);
         if (g.h0 != nullptr) {
-          sf_store16(g.h0, g.ldh0, g.M, 1, m0 + q * 32, col0, &h[0], stg, lane);
-          sf_store16(g.h0, g.ldh0, g.M, 1, m0 + q * 32, col0 + 16, &h[16], stg, lane);
+          if (g.tma_store) {
+            sf_store8_tma<0>(&tmap_h0, int(m0) + q * 32, col0, &h[0], stg, lane);
+            sf_store8_tma<0>(&tmap_h0, int(m0) + q * 32, col0 + 8, &h[8], stg, lane);
+          } else {
+            sf_store8(g.h0, g.ldh0, g.M, 1, m0 + q * 32, col0, &h[0], stg, lane);
+            sf_store8(g.h0, g.ldh0, g.M, 1, m0 + q * 32, col0 + 8, &h[8], stg, lane);
+          }
         }
       }
-      // ---- layer 1: this warp's 128-column half, 16 columns at a time ----
-      mbar_wait(a1_full, ti & 1);
+      // ---- layer 1: this warp's 64-column quarter, 16 columns at a time ----
+      mbar_wait_backoff<64>(a1_full, ti & 1);
       tc_fence_after();
       float hacc = 0.f;
 #pragma unroll 1
-      for (int cc = 0; cc < 8; ++cc) {
-        const int col0 = 128 * hf + 16 * cc;
+      for (int cc = 0; cc < 4; ++cc) {
+        const int col0 = 64 * part + 16 * cc;
         uint32_t v[16];
         tmem_ld16(tmem + uint32_t(NT) + lane_base + uint32_t(col0), v);
         tmem_ld_wait();
-        if (cc == 7) {
+        if (cc == 3) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(a1_empty);
@@ -236,76 +298,101 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SF_THREADS, 1)
         float h[16];
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 b4 = g.b1 ? __ldg(reinterpret_cast<const float4*>(g.b1 + col0) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.head_w + col0) + j4);
-          h[4 * j4 + 0] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 0]), dsc1, b4.x), p);
-          h[4 * j4 + 1] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 1]), dsc1, b4.y), p);
-          h[4 * j4 + 2] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 2]), dsc1, b4.z), p);
-          h[4 * j4 + 3] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 3]), dsc1, b4.w), p);
+          const float4 b4 = g.b1 ? ldg_keep(g.b1 + col0 + 4 * j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 w4 = ldg_keep(g.head_w + col0 + 4 * j4);
+          h[4 * j4 + 0] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 0]), dsc1, b4.x), c1, c2);
+          h[4 * j4 + 1] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 1]), dsc1, b4.y), c1, c2);
+          h[4 * j4 + 2] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 2]), dsc1, b4.z), c1, c2);
+          h[4 * j4 + 3] = sf_act<ACT>(fmaf(__uint_as_float(v[4 * j4 + 3]), dsc1, b4.w), c1, c2);
           hacc = fmaf(h[4 * j4 + 0], w4.x, fmaf(h[4 * j4 + 1], w4.y, fmaf(h[4 * j4 + 2], w4.z, fmaf(h[4 * j4 + 3], w4.w, hacc))));
         }
-        if (g.h1 != nullptr) sf_store16(g.h1, g.ldh1, g.M, g.h1_group, m0 + q * 32, col0, h, stg, lane);
+        if (g.h1 != nullptr) {
+          if (g.tma_store && g.h1_group == 1) {
+            // staged in the h0 operand ring, which is idle until the next tile's layer 0 (every layer-1 MMA has completed):
+            // 4 KB per warp = two chunks in flight, so a chunk only waits for the copy of the one before the previous
+            float* s1 = reinterpret_cast<float*>(smem + SF_OFF_H) + warp * 1024 + (cc & 1) * 512;
+            if (cc >= 2) {
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              __syncwarp();
+            }
+            sf_store16_tma(&tmap_h1, int(m0) + q * 32, col0, h, s1, lane);
+          } else {
+            if (g.tma_store) {      // the LSU path below reads the buffer back: the last TMA store must have read it
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              __syncwarp();
+            }
+            sf_store8(g.h1, g.ldh1, g.M, g.h1_group, m0 + q * 32, col0, &h[0], stg, lane);
+            sf_store8(g.h1, g.ldh1, g.M, g.h1_group, m0 + q * 32, col0 + 8, &h[8], stg, lane);
+          }
+        }
       }
-      // the two warps of a row quadrant combine their halves of the head's dot product
-      if (hf == 1) hx[row] = hacc;
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-      if (hf == 0 && m0 + row < g.M) g.sdf[m0 + row] = hacc + hx[row] + head_b;
+      // the four warps of a row quadrant combine their quarters of the head's dot product (fixed order: deterministic)
+      if (g.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      if (part != 0) stg[lane] = hacc;
+      asm volatile("bar.sync 1, %0;" ::"n"(SF_EPI_WARPS * 32) : "memory");
+      if (part == 0 && m0 + row < g.M) {
+        const float* o = stg_all + q * 32 * SF_STG_LD + lane;
+        g.sdf[m0 + row] = ((hacc + o[4 * 32 * SF_STG_LD]) + (o[8 * 32 * SF_STG_LD] + o[12 * 32 * SF_STG_LD])) + head_b;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(SF_EPI_WARPS * 32) : "memory");
     }
-  } else if (warp < EPI_WARPS + SF_PROD_WARPS) {
-    // ================= converters: one thread per row of this CTA's x tile =================
-    const int r = t - EPI_WARPS * 32;
-    const uint32_t rowb = uint32_t(r) * 128u;
-    const int sw = r & 7;
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // outstanding activation stores
+  } else if (warp < SF_EPI_WARPS + SF_PROD_WARPS) {
+    // ================= converters: two threads per row of this CTA's x tile (lane = half * 16 + row % 16) =================
+    // half 0 owns box 0 (k 0..31 -> fp16 chunks 0..3) and k 64..71, half 1 owns box 1 (k 32..63 -> chunks 4..7) and k 72..79
+    const int cw = warp - SF_EPI_WARPS, half = lane >> 4;
     uint32_t ti = 0;
     for (int64_t pt = pair; pt < ptiles; pt += npairs, ++ti) {
-      mbar_wait(x_raw, ti & 1);
-      float4 a[20];      // raw columns 0..79: boxes 0, 1 (8 chunks each) and the first 4 chunks of box 2
+      mbar_wait_backoff<256>(x_raw, ti & 1);
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const int r = cw * 32 + pass * 16 + (lane & 15);
+        const uint32_t rowb = uint32_t(r) * 128u;
+        const int sw = r & 7;
+        float4 a[10];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) a[c] = lds128(XR + rowb + (uint32_t(c ^ sw) << 4));
+        for (int c = 0; c < 8; ++c) a[c] = lds128(XR + half * PART + rowb + (uint32_t(c ^ sw) << 4));
 #pragma unroll
-      for (int c = 0; c < 8; ++c) a[8 + c] = lds128(XR + PART + rowb + (uint32_t(c ^ sw) << 4));
+        for (int c = 0; c < 2; ++c) a[8 + c] = lds128(XR + 2 * PART + rowb + (uint32_t((2 * half + c) ^ sw) << 4));
+        float ss = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) a[16 + c] = lds128(XR + 2 * PART + rowb + (uint32_t(c ^ sw) << 4));
-      float ss = 0.f;
+        for (int c = 0; c < 10; ++c) ss = fmaf(a[c].x, a[c].x, fmaf(a[c].y, a[c].y, fmaf(a[c].z, a[c].z, fmaf(a[c].w, a[c].w, ss))));
+        ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+        const float nrm = sqrtf(ss);
+        const float sx = pow2f(f16_scale_exp(nrm));
+        __syncwarp();                  // every raw chunk of the 16 rows is in registers: the tiles can be overwritten
 #pragma unroll
-      for (int c = 0; c < 20; ++c) ss = fmaf(a[c].x, a[c].x, fmaf(a[c].y, a[c].y, fmaf(a[c].z, a[c].z, fmaf(a[c].w, a[c].w, ss))));
-      const float nrm = sqrtf(ss);
-      const float sx = pow2f(f16_scale_exp(nrm));
-      // logical fp16 chunk j (8 k) of k-block 0 = raw chunks 2 j, 2 j + 1
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint32_t hh[4], ll[4];
-        split_f16x2(a[2 * j].x * sx, a[2 * j].y * sx, hh[0], ll[0]);
-        split_f16x2(a[2 * j].z * sx, a[2 * j].w * sx, hh[1], ll[1]);
-        split_f16x2(a[2 * j + 1].x * sx, a[2 * j + 1].y * sx, hh[2], ll[2]);
-        split_f16x2(a[2 * j + 1].z * sx, a[2 * j + 1].w * sx, hh[3], ll[3]);
-        const uint32_t phys = uint32_t(j ^ sw) << 4;
-        sts128u(XR + rowb + phys, hh[0], hh[1], hh[2], hh[3]);
-        if (NPROD == 3) sts128u(XR + PART + rowb + phys, ll[0], ll[1], ll[2], ll[3]);
+        for (int j = 0; j < 5; ++j) {
+          uint32_t hh[4], ll[4];
+          split_f16x2_bounded(a[2 * j].x * sx, a[2 * j].y * sx, hh[0], ll[0]);
+          split_f16x2_bounded(a[2 * j].z * sx, a[2 * j].w * sx, hh[1], ll[1]);
+          split_f16x2_bounded(a[2 * j + 1].x * sx, a[2 * j + 1].y * sx, hh[2], ll[2]);
+          split_f16x2_bounded(a[2 * j + 1].z * sx, a[2 * j + 1].w * sx, hh[3], ll[3]);
+          if (j < 4) {
+            // k-block 0: logical fp16 chunk 4 half + j of the hi tile (box 0's bytes) and of the lo tile (box 1's bytes)
+            const uint32_t phys = uint32_t((4 * half + j) ^ sw) << 4;
+            sts128u(XR + rowb + phys, hh[0], hh[1], hh[2], hh[3]);
+            if (NPROD == 3) sts128u(XR + PART + rowb + phys, ll[0], ll[1], ll[2], ll[3]);
+          } else {
+            // k-block 1 (k 64..79): hi in logical chunks 0, 1 and lo in chunks 2, 3 of the same 128-byte row
+            sts128u(XR + 2 * PART + rowb + (uint32_t(half ^ sw) << 4), hh[0], hh[1], hh[2], hh[3]);
+            if (NPROD == 3) sts128u(XR + 2 * PART + rowb + (uint32_t((half + 2) ^ sw) << 4), ll[0], ll[1], ll[2], ll[3]);
+          }
+        }
+        if (half == 0) xnorm[(ti & 1) * TM + r] = nrm;
       }
-      // k-block 1 (k 64..79): hi in logical chunks 0, 1 and lo in chunks 2, 3 of the same 128-byte row
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        uint32_t hh[4], ll[4];
-        split_f16x2(a[16 + 2 * j].x * sx, a[16 + 2 * j].y * sx, hh[0], ll[0]);
-        split_f16x2(a[16 + 2 * j].z * sx, a[16 + 2 * j].w * sx, hh[1], ll[1]);
-        split_f16x2(a[17 + 2 * j].x * sx, a[17 + 2 * j].y * sx, hh[2], ll[2]);
-        split_f16x2(a[17 + 2 * j].z * sx, a[17 + 2 * j].w * sx, hh[3], ll[3]);
-        sts128u(XR + 2 * PART + rowb + (uint32_t(j ^ sw) << 4), hh[0], hh[1], hh[2], hh[3]);
-        if (NPROD == 3) sts128u(XR + 2 * PART + rowb + (uint32_t((j + 2) ^ sw) << 4), ll[0], ll[1], ll[2], ll[3]);
-      }
-      xnorm[(ti & 1) * TM + r] = nrm;
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(x_full);
     }
-  } else if (warp == EPI_WARPS + SF_PROD_WARPS) {
+  } else if (warp == SF_EPI_WARPS + SF_PROD_WARPS) {
     // ================= loader =================
     if (lane == 0) {
       uint32_t bi = 0, xi = 0;
       auto load_x = [&](int64_t pt) {
         const int m0 = int(pt * 2 * TM + rank * TM);
-        mbar_wait(x_empty, (xi & 1) ^ 1);
+        mbar_wait_backoff<128>(x_empty, (xi & 1) ^ 1);
         mbar_arrive_expect_tx(x_raw, uint32_t(3 * PART));
         tma_load_2d(XR, &tmap_x, 0, m0, x_raw);
         tma_load_2d(XR + PART, &tmap_x, TK, m0, x_raw);
@@ -314,7 +401,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SF_THREADS, 1)
       };
       auto load_b = [&](const CUtensorMap* map, int kb) {
         const uint32_t s = bi % SF_BSTAGES;
-        mbar_wait(b_empty + 8 * s, ((bi / SF_BSTAGES) & 1) ^ 1);
+        mbar_wait_backoff<128>(b_empty + 8 * s, ((bi / SF_BSTAGES) & 1) ^ 1);
         if (rank == 0) mbar_arrive_expect_tx(b_full + 8 * s, uint32_t((NPROD == 3 ? 4 : 2) * SF_HB));
         const int row_hi = kb * 2 * NT + int(rank) * 128;
         tma_load_2d_pair(BR + s * SF_BSTAGE, map, 0, row_hi, b_full + 8 * s);
@@ -335,14 +422,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SF_THREADS, 1)
         }
       }
     }
-  } else if (warp == EPI_WARPS + SF_PROD_WARPS + 1 && rank == 0) {
+  } else if (warp == SF_EPI_WARPS + SF_PROD_WARPS + 1 && rank == 0) {
     // ================= MMA issuer (leader CTA) =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(NT, 2 * TM);
       uint32_t bi = 0;
       auto mma_block = [&](uint64_t dah, uint64_t dal, int ksteps, uint32_t d, bool first) {
         const uint32_t s = bi % SF_BSTAGES;
-        mbar_wait(b_full + 8 * s, (bi / SF_BSTAGES) & 1);
+        mbar_wait_backoff<32>(b_full + 8 * s, (bi / SF_BSTAGES) & 1);
         tc_fence_after();
         const uint64_t dbh = make_desc(BR + s * SF_BSTAGE, 16, 1024), dbl = make_desc(BR + s * SF_BSTAGE + SF_HB, 16, 1024);
         for (int j = 0; j < ksteps; ++j) {
@@ -360,8 +447,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SF_THREADS, 1)
         ++bi;
       };
       auto layer0 = [&](uint32_t ti) {
-        mbar_wait(x_full, ti & 1);
-        mbar_wait(a0_empty, (ti & 1) ^ 1);
+        mbar_wait_backoff<32>(x_full, ti & 1);
+        mbar_wait_backoff<32>(a0_empty, (ti & 1) ^ 1);
         tc_fence_after();
         mma_block(make_desc(XR, 16, 1024), make_desc(XR + PART, 16, 1024), TK16 / 16, tmem, true);
         if (ks1 > 0) mma_block(make_desc(XR + 2 * PART, 16, 1024), make_desc(XR + 2 * PART, 16, 1024) + 2, ks1, tmem, false);
@@ -371,11 +458,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SF_THREADS, 1)
       if (pair < ptiles) layer0(0);
       uint32_t ti = 0;
       for (int64_t pt = pair; pt < ptiles; pt += npairs, ++ti) {
-        mbar_wait(a1_empty, (ti & 1) ^ 1);
+        mbar_wait_backoff<32>(a1_empty, (ti & 1) ^ 1);
         tc_fence_after();
         for (int c = 0; c < 4; ++c) {
           const uint32_t slot = c & 1, use = 2 * ti + (c >> 1);
-          mbar_wait(h_full + 8 * slot, use & 1);
+          mbar_wait_backoff<32>(h_full + 8 * slot, use & 1);
           tc_fence_after();
           const uint32_t hb = HR + slot * SF_HSLOT;
           mma_block(make_desc(hb, 16, 1024), make_desc(hb + PART, 16, 1024), TK16 / 16, tmem + NT, c == 0);
@@ -409,9 +496,29 @@ static bool make_x_map(const float* x, int64_t ld, int64_t rows, int cols, CUten
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Tensor map of an activation output: [M rows, 256 floats], box 8 floats x 32 rows, no swizzle (the epilogue warps' store blocks)
+static bool make_out_map(float* y, int64_t ld, int64_t rows, int box_cols, CUtensorMap* map) {
+  TensorMapEncodeFn encode = tensor_map_encoder();
+  if (encode == nullptr || rows >= (int64_t(1) << 31)) return false;
+  const cuuint64_t dims[2] = {cuuint64_t(NT), cuuint64_t(rows)};
+  const cuuint64_t strides[1] = {cuuint64_t(ld) * sizeof(float)};
+  const cuuint32_t box[2] = {cuuint32_t(box_cols), 32};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int ACT, int NPROD>
-static int launch_sdf_fused(const SdfFusedArgs& g, const CUtensorMap& mx, const CUtensorMap& m0, const CUtensorMap& m1,
+static int launch_sdf_fused(const SdfFusedArgs& g_in, const CUtensorMap& mx, const CUtensorMap& m0, const CUtensorMap& m1,
                             cudaStream_t s) {
+  SdfFusedArgs g = g_in;
+  CUtensorMap mh0, mh1;
+  memset(&mh0, 0, sizeof(mh0));
+  memset(&mh1, 0, sizeof(mh1));
+  static int use_tma_store = -1;
+  if (use_tma_store < 0) { const char* e = getenv("MMSB_SDF_TMA_STORE"); use_tma_store = e ? atoi(e) : 1; }
+  g.tma_store = use_tma_store && (g.h0 == nullptr || make_out_map(g.h0, g.ldh0, g.M, SF_STG_LD, &mh0)) &&
+                (g.h1 == nullptr || g.h1_group > 1 || make_out_map(g.h1, g.ldh1, g.M, 16, &mh1));
   static PerDeviceFlag flags;
   bool& configured = flags();
   auto kern = sdf_fused_fwd_kernel<ACT, NPROD>;
@@ -427,7 +534,7 @@ static int launch_sdf_fused(const SdfFusedArgs& g, const CUtensorMap& mx, const 
   cfg.blockDim = dim3(SF_THREADS);
   cfg.dynamicSmemBytes = SF_SMEM;
   cfg.stream = s;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g, mx, m0, m1);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g, mx, m0, m1, mh0, mh1);
   if (e != cudaSuccess) {
     set_error("sdf_net_fwd_fused: cluster launch failed: %s", cudaGetErrorString(e));
     return MMSB_E_CUDA;

@@ -89,6 +89,32 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// The same wait with a back-off: a warp that polls in a tight loop takes issue slots from the warps that work (measured
+// on the fused SDF kernel: a third of all issued instructions were polling).  SLEEP_NS ~ the latency the waiter can
+// afford: tens of ns on the MMA hand-shake path, hundreds for prefetching roles.
+template <int SLEEP_NS>
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done) {
+      __nanosleep(SLEEP_NS);
+      if (spins > (1u << 22)) {
+        printf("mms_b200 tcgen05: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+               bar, parity);
+        __trap();
+      }
+    }
+  }
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -169,6 +195,13 @@ __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint
   b = fminf(fmaxf(b, -65504.f), 65504.f);
   // round to 11 significant bits with one integer add and one mask (exact for fp16-normal magnitudes; below 2^-14 the
   // conversion rounds again, an absolute error of at most 2^-25 of the scaled value, i.e. 2^-39 of the tensor's max)
+  const float ha = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xFFFFE000u);
+  const float hb = __uint_as_float((__float_as_uint(b) + 0x1000u) & 0xFFFFE000u);
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(hb), "f"(ha));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
+}
+// the same split for values the caller has bounded below 2^16 in magnitude (no clamp)
+__device__ __forceinline__ void split_f16x2_bounded(float a, float b, uint32_t& hi, uint32_t& lo) {
   const float ha = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xFFFFE000u);
   const float hb = __uint_as_float((__float_as_uint(b) + 0x1000u) & 0xFFFFE000u);
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(hb), "f"(ha));

@@ -681,24 +681,42 @@ class SdfNetFn(torch.autograd.Function):
         # mode 2: fp16 split for the forward products it covers (every row of one call takes the same path: centre, taps
         # and sampler evaluations keep sharing one arithmetic), 3xTF32 for the backward products
         mode2 = prec == 2
-        amaxes = torch.zeros((2,), device=dev, dtype=torch.float32) if mode2 else None
-        p0 = layer_precision(x2, ws[0].shape[0]) if mode2 else prec
-        h0 = linear_fwd_tc(x2, packed_weight(w0, False, p0), bs[0], ws[0].shape[0], act, act_param, p0,
-                           y_amax=amaxes[0:1] if mode2 else None)
-        sdf = torch.zeros((n,), device=dev, dtype=torch.float32)
-        keep_h1 = need_grad or n_full > 0
-        h1 = torch.empty((n, hid), device=dev, dtype=torch.float32) if keep_h1 else None
-        p1 = layer_precision(h0, hid) if mode2 else prec
-        call("mmsb_linear_fwd_head_tc", ptr(h0), _i64(h0.stride(0)), ptr(packed_weight(w1, False, p1)), ptr(bs[1]), ptr(h1),
-             _i64(hid), _i64(n), _i32(ws[1].shape[1]), _i32(hid), _i32(act), _f32(act_param), _i32(p1), ptr(ws[2]),
-             ptr(bs[2]), ptr(sdf), ptr(amaxes[0:1]) if p1 == 2 else None, ptr(amaxes[1:2]) if mode2 and keep_h1 else None,
-             stream_ptr())
-        geo = None
-        if n_full > 0:
-            h1c = h1[0::group] if group > 1 else h1[:n_full]
-            p2 = layer_precision(h1c, g_dim) if mode2 else prec
-            geo = linear_fwd_tc(h1c, packed_weight(w2, False, p2, rows=(1, g_dim + 1)), bs[2][1:], g_dim, 0, 1.0, p2,
-                                x_amax=amaxes[1:2] if p2 == 2 else None)
+        if sdf_fused_eligible(x2, ws[0], ws[1], act):
+            # ONE kernel for layer 0 -> layer 1 -> sdf head (h0 stays on chip between the layers); fp16-split products
+            # (fp32-accurate) in modes 2 / 3, a single fp16 pass in the fast mode 1.  h0 / h1 are written out only for the
+            # backward kernels; without a backward only the centre rows' h1 is (the geometry features' input).
+            h0 = torch.empty((n, hid), device=dev, dtype=torch.float32) if need_grad else None
+            h1, h1_group = None, 1
+            if need_grad or (n_full > 0 and group == 1):
+                h1 = torch.empty((n, hid), device=dev, dtype=torch.float32)
+            elif n_full > 0:
+                h1, h1_group = torch.empty((n_full, hid), device=dev, dtype=torch.float32), group
+            sdf = sdf_net_fwd_fused(x2, w0, bs[0], w1, bs[1], ws[2], bs[2], act, act_param, 1 if prec == 1 else 3, h0=h0, h1=h1,
+                                    h1_group=h1_group)
+            geo = None
+            if n_full > 0:
+                h1c = h1 if h1_group > 1 else (h1[0::group] if group > 1 else h1[:n_full])
+                p2 = 1 if prec == 1 else 3
+                geo = linear_fwd_tc(h1c, packed_weight(w2, False, p2, rows=(1, g_dim + 1)), bs[2][1:], g_dim, 0, 1.0, p2)
+        else:
+            amaxes = torch.zeros((2,), device=dev, dtype=torch.float32) if mode2 else None
+            p0 = layer_precision(x2, ws[0].shape[0]) if mode2 else prec
+            h0 = linear_fwd_tc(x2, packed_weight(w0, False, p0), bs[0], ws[0].shape[0], act, act_param, p0,
+                               y_amax=amaxes[0:1] if mode2 else None)
+            sdf = torch.zeros((n,), device=dev, dtype=torch.float32)
+            keep_h1 = need_grad or n_full > 0
+            h1 = torch.empty((n, hid), device=dev, dtype=torch.float32) if keep_h1 else None
+            p1 = layer_precision(h0, hid) if mode2 else prec
+            call("mmsb_linear_fwd_head_tc", ptr(h0), _i64(h0.stride(0)), ptr(packed_weight(w1, False, p1)), ptr(bs[1]), ptr(h1),
+                 _i64(hid), _i64(n), _i32(ws[1].shape[1]), _i32(hid), _i32(act), _f32(act_param), _i32(p1), ptr(ws[2]),
+                 ptr(bs[2]), ptr(sdf), ptr(amaxes[0:1]) if p1 == 2 else None, ptr(amaxes[1:2]) if mode2 and keep_h1 else None,
+                 stream_ptr())
+            geo = None
+            if n_full > 0:
+                h1c = h1[0::group] if group > 1 else h1[:n_full]
+                p2 = layer_precision(h1c, g_dim) if mode2 else prec
+                geo = linear_fwd_tc(h1c, packed_weight(w2, False, p2, rows=(1, g_dim + 1)), bs[2][1:], g_dim, 0, 1.0, p2,
+                                    x_amax=amaxes[1:2] if p2 == 2 else None)
         if mode2:
             prec = 3
         ctx.cfg = (n, n_full, group, act, act_param, prec, in_dim, x.shape)
@@ -757,7 +775,7 @@ def sdf_fused_eligible(x2, w0, w1, act) -> bool:
     """Shapes mmsb_sdf_net_fwd_fused covers (include/mms_b200.h): 64 < in_dim <= 80, hidden width 256, ReLU / Softplus,
     16-byte aligned rows."""
     return (SDF_FUSED != 0 and MLP_PRECISION in (1, 2, 3) and 64 < x2.shape[1] <= 80 and tuple(w1.shape) == (256, 256)
-            and w0.shape[0] == 256 and act in (ACT["relu"], ACT["softplus"]) and x2.stride(1) == 1 and x2.stride(0) % 4 == 0
+            and w0.shape[0] == 256 and act in (ACT["ReLU"], ACT["Softplus"]) and x2.stride(1) == 1 and x2.stride(0) % 4 == 0
             and x2.data_ptr() % 16 == 0)
 
 
