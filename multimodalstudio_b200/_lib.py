@@ -13,7 +13,7 @@ import threading
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _REPO_ROOT = os.path.dirname(_PKG_DIR)
 HEADER_PATH = os.path.join(_REPO_ROOT, "include", "mms_b200.h")
-LIB_PATH = os.path.join(_PKG_DIR, "libmms_b200.so")
+LIB_PATH = os.environ.get("MMSB_LIB") or os.path.join(_PKG_DIR, "libmms_b200.so")   # MMSB_LIB: dev builds only
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
 MMSB_MAX_LEVELS = 32

@@ -916,12 +916,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_rows_kernel(const __grid_consta
         const int w = tile_width(n_pad, nt);
         const uint32_t idesc = make_idesc_tf32(w, false);
         const uint32_t acc = ti & 1;
-        mbar_wait(bar_tempty + 8 * acc, ((ti >> 1) & 1) ^ 1);
+        mbar_wait_spin(bar_tempty + 8 * acc, ((ti >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem + acc * NT;
         for (int kb = 0; kb < g.nkb; ++kb, ++it) {
           const uint32_t s = it % S;
-          mbar_wait(bar_full + 8 * s, (it / S) & 1);
+          mbar_wait_spin(bar_full + 8 * s, (it / S) & 1);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + s * STAGE);
           const uint32_t b_hi = a_hi + NPARTS * PART;
@@ -1162,12 +1162,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
       uint32_t it = 0, ti = 0;
       for (int64_t pt = pair; pt < total_ptiles; pt += npairs, ++ti) {
         const uint32_t acc = ti & 1;
-        mbar_wait(bar_tempty + 8 * acc, ((ti >> 1) & 1) ^ 1);
+        mbar_wait_spin(bar_tempty + 8 * acc, ((ti >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem + acc * NT;
         for (int kb = 0; kb < g.nkb; ++kb, ++it) {
           const uint32_t s = it % S;
-          mbar_wait(bar_full + 8 * s, (it / S) & 1);
+          mbar_wait_spin(bar_full + 8 * s, (it / S) & 1);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + s * STAGE), b_hi = a_hi + 2 * PART;
           const uint64_t dah = make_desc(a_hi, 16, 1024), dal = make_desc(a_hi + PART, 16, 1024);
@@ -1465,7 +1465,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradArgs
         if (PAIR) idesc = (1u << 4) | (2u << 7) | (2u << 10) | (3u << 15) | (uint32_t(NT >> 3) << 17) | (uint32_t((2 * TM) >> 4) << 24);
         for (int kb = 0; kb < nkb; ++kb) {
           const uint32_t s = kb % S;
-          mbar_wait(bar_full + 8 * s, (kb / S) & 1);
+          mbar_wait_spin(bar_full + 8 * s, (kb / S) & 1);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + s * STAGE);
           const uint32_t b_hi = a_hi + NPARTS * PART;

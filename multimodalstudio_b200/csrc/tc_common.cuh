@@ -70,30 +70,13 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 // Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t spins = 0; !done; ++spins) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && spins > (1u << 24)) {
-      printf("mms_b200 tcgen05: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-             bar, parity);
-      __trap();
-    }
-  }
-}
-// The same wait with a back-off: a warp that polls in a tight loop takes issue slots from the warps that work (measured
-// on the fused SDF kernel: a third of all issued instructions were polling).  SLEEP_NS ~ the latency the waiter can
-// afford: tens of ns on the MMA hand-shake path, hundreds for prefetching roles.
+// MMSB_TC_WAIT_BACKOFF_NS > 0: the polling loop sleeps between tries (see mbar_wait_backoff); the MMA issuers keep the
+// tight loop (mbar_wait_spin): their wake-up latency is on the tensor pipe's critical path.
+#ifndef MMSB_TC_WAIT_BACKOFF_NS
+#define MMSB_TC_WAIT_BACKOFF_NS 0
+#endif
 template <int SLEEP_NS>
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_impl(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   for (uint32_t spins = 0; !done; ++spins) {
     asm volatile(
@@ -106,8 +89,8 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
         : "r"(bar), "r"(parity)
         : "memory");
     if (!done) {
-      __nanosleep(SLEEP_NS);
-      if (spins > (1u << 22)) {
+      if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+      if (spins > (SLEEP_NS > 0 ? (1u << 22) : (1u << 24))) {
         printf("mms_b200 tcgen05: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
                bar, parity);
         __trap();
@@ -115,6 +98,13 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
     }
   }
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_impl<MMSB_TC_WAIT_BACKOFF_NS>(bar, parity); }
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) { mbar_wait_impl<0>(bar, parity); }
+// The same wait with a back-off: a warp that polls in a tight loop takes issue slots from the warps that work (measured
+// on the fused SDF kernel: a third of all issued instructions were polling).  SLEEP_NS ~ the latency the waiter can
+// afford: tens of ns on the MMA hand-shake path, hundreds for prefetching roles.
+template <int SLEEP_NS>
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) { mbar_wait_impl<SLEEP_NS>(bar, parity); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }

@@ -594,6 +594,58 @@ def test_sdf_net_fused_head_vs_fp64(n, n_full, group):
         assert_close(a, r, rtol=3e-5, atol=1e-7, what=name)
 
 
+@pytest.mark.parametrize("n,act,xs", [(1, "Softplus", 1.0), (300, "Softplus", 1.0), (5001, "Softplus", 1e-4), (5001, "Softplus", 300.0),
+                                       (40000, "ReLU", 1.0), (70001, "Softplus", 1.0)])
+def test_sdf_net_fwd_fused_vs_fp64(n, act, xs):
+    """mmsb_sdf_net_fwd_fused (layer 0 -> layer 1 -> sdf head in one kernel, h0 on chip as fp16 hi / lo with per-row
+    power-of-two scales) against fp64: sdf and the stored activations at 5e-6 of their max for operand scales from 1e-4
+    to 3e2 and columns 100x apart inside a row; stored / not stored / grouped variants bit-identical; the single-pass
+    mode (products = 1) inside the fast-mode band."""
+    from multimodalstudio_b200 import ops
+    torch.manual_seed(n)
+    x = torch.randn(n, 72, device=DEV).mul_(0.5 * xs)[:, :71]
+    x[:, :32] *= 1e-2                              # hash features next to positions / PE
+    w0 = torch.randn(256, 71, device=DEV) * 0.1 / xs
+    b0 = torch.randn(256, device=DEV) * 0.1
+    w1 = torch.randn(256, 256, device=DEV) * 0.05
+    b1 = torch.randn(256, device=DEV) * 0.1
+    w2 = torch.randn(257, 256, device=DEV) * 0.05
+    b2 = torch.randn(257, device=DEV) * 0.1
+    a, beta = ops.ACT[act], 100.0
+    f = (lambda z: torch.nn.functional.softplus(z, beta=beta)) if act == "Softplus" else torch.relu
+    h0r = f(x.double() @ w0.double().T + b0.double())
+    h1r = f(h0r @ w1.double().T + b1.double())
+    sdfr = h1r @ w2[0].double() + b2[0].double()
+    h0 = torch.full((n, 256), float("nan"), device=DEV)
+    h1 = torch.full((n, 256), float("nan"), device=DEV)
+    sdf = ops.sdf_net_fwd_fused(x, w0, b0, w1, b1, w2, b2, a, beta, 3, h0=h0, h1=h1)
+    assert_close(sdf, sdfr, rtol=5e-6, what="sdf")
+    assert_close(h0, h0r, rtol=5e-6, what="h0")
+    assert_close(h1, h1r, rtol=5e-6, what="h1")
+    assert torch.equal(sdf, ops.sdf_net_fwd_fused(x, w0, b0, w1, b1, w2, b2, a, beta, 3)), "stored / not stored differ"
+    g = 5
+    h1g = torch.full(((n + g - 1) // g, 256), float("nan"), device=DEV)
+    sdf_g = ops.sdf_net_fwd_fused(x, w0, b0, w1, b1, w2, b2, a, beta, 3, h1=h1g, h1_group=g)
+    assert torch.equal(sdf, sdf_g) and torch.equal(h1g, h1[0::g]), "grouped h1 store differs"
+    fast = ops.sdf_net_fwd_fused(x, w0, b0, w1, b1, w2, b2, a, beta, 1)
+    assert_close(fast, sdfr, rtol=5e-3, what="sdf (single fp16 pass)")
+
+
+def test_sdf_net_fwd_fused_rejects_other_shapes():
+    from multimodalstudio_b200 import ops
+    x = torch.randn(64, 40, device=DEV)
+    w0, w1, w2 = torch.randn(256, 40, device=DEV), torch.randn(256, 256, device=DEV), torch.randn(257, 256, device=DEV)
+    b = torch.zeros(257, device=DEV)
+    with pytest.raises(ValueError):
+        ops.sdf_net_fwd_fused(x, w0, b[:256], w1, b[:256], w2, b, ops.ACT["Softplus"], 100.0, 3)
+    x = torch.randn(64, 72, device=DEV)[:, :71]
+    w0 = torch.randn(256, 71, device=DEV)
+    with pytest.raises(ValueError):
+        ops.sdf_net_fwd_fused(x, w0, b[:256], w1, b[:256], w2, b, ops.ACT["Sigmoid"], 1.0, 3)
+    with pytest.raises(ValueError):
+        ops.sdf_net_fwd_fused(x, w0, b[:256], w1, b[:256], w2, b, ops.ACT["Softplus"], 100.0, 2)
+
+
 def test_decimated_losses_golden():
     """Preset grid_decimated: LossManager's per_channel_probability losses against the reference fixture (the channel
     draws of the reference are injected), value and gradient; and the preset builds + draws on its own."""
