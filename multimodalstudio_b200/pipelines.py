@@ -161,6 +161,19 @@ def all_reduce_flat(flat: torch.Tensor, group=None):
     return flat
 
 
+def all_reduce_optimizers(optimizers, group=None, mean: bool = True):
+    """ONE summing all-reduce per optimizer over its flat gradient buffer (`FlatAdamW.grad`).  `mean=True` (weak scaling,
+    every rank a full batch with its own mean losses — the reference's DDP semantics): the 1 / world size of DDP's
+    average is folded into the optimizer kernel's gradient read (FlatAdamW.prescale), no extra pass over the 138 MB.
+    `mean=False` (strong scaling, losses already normalised by the global counts): the sum IS the single-batch gradient."""
+    import torch.distributed as dist
+    ws = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    for opt in optimizers.values():
+        opt.prescale = 1.0 / ws if (mean and ws > 1) else 1.0
+        if ws > 1:
+            all_reduce_flat(opt.grad, group)
+
+
 class FlatAdamW:
     """One AdamW "optimizer" of the reference (engine/optimizers.py, method_configs.py:260-269) over a flat
     fp32 buffer: parameters and gradients are views into two contiguous tensors, so zero-grad is one memset,
@@ -353,16 +366,8 @@ class RawPipeline:
         return 1
 
     def all_reduce_gradients(self, mean: bool = True):
-        """The gradient exchange of the reference's DDP: ONE summing NCCL all-reduce per optimizer over
-        its flat gradient buffer.  `mean=True` (weak scaling, every rank a full batch with its own mean losses): the
-        1 / world size of DDP's average is folded into the optimizer kernel's gradient read (FlatAdamW.prescale), no
-        extra pass over the 138 MB.  `mean=False` (strong scaling, losses already normalised by the global counts): the
-        sum is the single-batch gradient."""
-        ws = self._world()
-        for opt in self.optimizers.values():
-            opt.prescale = 1.0 / ws if (mean and ws > 1) else 1.0
-            if ws > 1:
-                all_reduce_flat(opt.grad, self.process_group)
+        """The gradient exchange of the reference's DDP, see `all_reduce_optimizers`."""
+        all_reduce_optimizers(self.optimizers, self.process_group, mean)
 
     def optimizer_step(self, step):
         f = multistep_warmup_factor(step, self.max_num_iterations)

@@ -1,8 +1,8 @@
 """CPU, gloo, world size 2: the multi-GPU scheme of DESIGN.md §6 ("strong" mode) — ONE global ray batch
 split contiguously over the ranks by the product's `pipelines.ShardPlan` (ragged modality counts, micro-batches on
 each rank), every loss normalised by the GLOBAL count, gradients accumulated over micro-batches in a flat buffer and
-combined by the product's `pipelines.all_reduce_flat` (one summing all-reduce) — reproduces the gradient of the
-unsharded batch.  Also the "weak" mode (per-rank mean losses, summing all-reduce, 1 / world size folded into the
+combined by the product's `pipelines.all_reduce_optimizers` over `FlatAdamW`'s flat buffer (one summing all-reduce; the
+same objects and calls `RawPipeline.all_reduce_gradients` makes on NCCL) — reproduces the gradient of the unsharded batch.  Also the "weak" mode (per-rank mean losses, summing all-reduce, 1 / world size folded into the
 optimizer's gradient read = FlatAdamW.prescale).  The arithmetic of a shard is the CPU oracle here (there is no GPU in
 this container; the same plan drives the CUDA path in tests/test_gpu_model.py::test_sharded_*)."""
 import os
@@ -39,11 +39,11 @@ def _setup():
     return O, orc, params, rays, tgt
 
 
-def _flat_grad_of_plan(O, orc, params, rays, tgt, plan, geometry_count):
-    """Runs every micro-batch of `plan` through the oracle with the product's loss normalisation and accumulates the
-    gradients in one flat buffer (what FlatAdamW.gather_grads(accumulate=True) does on the device)."""
-    n_flat = sum(p.numel() for p in params)
-    flat, total_sum = torch.zeros(n_flat), 0.0
+def _flat_grad_of_plan(O, orc, opt, rays, tgt, plan, geometry_count):
+    """Runs every micro-batch of `plan` through the oracle with the product's loss normalisation; the gradients are
+    accumulated by the PRODUCT's optimizer object (pipelines.FlatAdamW: detach_grads -> backward -> gather_grads into
+    its flat buffer, exactly what RawPipeline.forward_backward does around the CUDA path)."""
+    total_sum = 0.0
     for j in range(len(plan)):
         part, tpart, scales = plan.slice(j, rays), plan.slice(j, tgt), plan.loss_scales(j)
         total, grads = 0.0, []
@@ -56,12 +56,11 @@ def _flat_grad_of_plan(O, orc, params, rays, tgt, plan, geometry_count):
         g = torch.cat(grads, 0)
         eik_sum = ((g.norm(dim=-1) - 1.0) ** 2).sum()
         total = total + 0.1 * eik_sum / geometry_count                              # local sum / GLOBAL count
-        for p in params:
-            p.grad = None
+        opt.detach_grads()
         total.backward()
-        flat += torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+        opt.gather_grads(accumulate=j > 0)
         total_sum += float(total.detach())
-    return total_sum, flat
+    return total_sum, opt.grad
 
 
 def _global_count(O, rays):
@@ -72,18 +71,25 @@ def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(2)
-    from multimodalstudio_b200.pipelines import ShardPlan, all_reduce_flat
+    from multimodalstudio_b200.pipelines import FlatAdamW, ShardPlan, all_reduce_flat, all_reduce_optimizers
     O, orc, params, rays, tgt = _setup()
+    opt = FlatAdamW(params, max_norm=None)
     plan = ShardPlan(COUNTS, world, rank, max_rays_per_micro=4)
     assert len(plan) == 2
     # the global in-sphere sample count: local count, summed over the ranks (as RawPipeline.train_step_sharded does)
     local = plan.local_slice(rays)
     cnt = torch.tensor([_global_count(O, local)])
     all_reduce_flat(cnt)
-    total, flat = _flat_grad_of_plan(O, orc, params, rays, tgt, plan, float(cnt))
-    all_reduce_flat(flat)                                      # the ONE data-path collective: a summing all-reduce
+    total, flat = _flat_grad_of_plan(O, orc, opt, rays, tgt, plan, float(cnt))
+    all_reduce_optimizers({"fields": opt}, mean=False)         # the ONE data-path collective: a summing all-reduce
+    assert opt.prescale == 1.0
     t = torch.tensor([total])
     all_reduce_flat(t)
+    flat = flat.clone()
+    # weak mode on the same buffers: the all-reduce still SUMS, DDP's mean is the optimizer's prescale
+    before = opt.grad.clone()
+    all_reduce_optimizers({"fields": opt}, mean=True)
+    assert opt.prescale == 1.0 / world and torch.allclose(opt.grad, before * world)
     if rank == 0:
         q.put((float(t), flat, float(cnt)))
     dist.barrier()
@@ -106,11 +112,11 @@ def test_sharded_global_batch_plus_allreduce_equals_single_process():
     threads = torch.get_num_threads()
     torch.set_num_threads(2)
     sys.path.insert(0, ROOT)
-    from multimodalstudio_b200.pipelines import ShardPlan
+    from multimodalstudio_b200.pipelines import FlatAdamW, ShardPlan
     O, orc, params, rays, tgt = _setup()
     cnt1 = _global_count(O, rays)
     assert cnt1 == cnt2
-    loss1, flat1 = _flat_grad_of_plan(O, orc, params, rays, tgt, ShardPlan(COUNTS), cnt1)      # one rank, one batch
+    loss1, flat1 = _flat_grad_of_plan(O, orc, FlatAdamW(params, max_norm=None), rays, tgt, ShardPlan(COUNTS), cnt1)      # one rank, one batch
     assert abs(loss1 - loss2) < 1e-6 * max(1.0, abs(loss1)), (loss1, loss2)
     err = float((flat1 - flat2).abs().max() / flat1.abs().max())
     torch.set_num_threads(threads)
