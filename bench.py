@@ -311,9 +311,10 @@ def main():
     from multimodalstudio_b200.pipelines import ShardPlan
     if args.mlp_precision is not None:
         _ops.set_mlp_precision(args.mlp_precision)
-    LAYERS = {0: "fp32 SIMT GEMM", 1: "tcgen05 single-pass TF32 (1e-2 band; not the reported configuration)",
+    FUSED = " + the SDF network's forward (layer 0 -> layer 1 -> sdf head) as ONE kernel with h0 kept on chip, " if _ops.SDF_FUSED else ""
+    LAYERS = {0: "fp32 SIMT GEMM", 1: "tcgen05 single-pass TF32" + (FUSED + "single fp16 pass" if FUSED else "") + " (1e-2 band; not the reported configuration)",
               2: "tcgen05 2-term fp16 split (hi + lo, per-tensor power-of-two scaling) for the forward products of the CTA-pair shapes, 3xTF32 elsewhere; fp32 in / out",
-              3: "tcgen05 3xTF32, fp32 in / out (1e-5 band)"}
+              3: "tcgen05 3xTF32" + (FUSED + "2-term fp16 split with per-row power-of-two scales (three kind::f16 MMAs per product, fp32-accurate)" if FUSED else "") + ", fp32 in / out (1e-5 band)"}
     cfg_out["layers"] = LAYERS[_ops.MLP_PRECISION]
     cfg_out["micro_batches_per_rank"] = len(ShardPlan(split_rays(wl["rays"] if strong else wl["weak_rays"], wl["modalities"]),
                                                       world if strong else 1, rank if strong else 0, max_rays_per_micro=wl["micro"]))
@@ -494,8 +495,21 @@ def main():
         cnt = {k: 0 for k in flops}
         hb = {"mmsb_hashgrid_fwd": [0.0, 0.0, 0], "mmsb_hashgrid_bwd": [0.0, 0.0, 0]}
         shapes = {}     # (class, rows, in, out) -> [flops, ms, launches] of the instrumented micro-batch
+        fused = [0.0, 0.0, 0, 0.0, 0]       # flops, ms, launches of the fused SDF forward; ms and rows of its largest launch
         for name, ms, a in rec:
-            if name in LAYER:
+            if name == "mmsb_sdf_net_fwd_fused":
+                n, k, o = a[2].value, a[3].value, a[4].value
+                f_ = 2.0 * n * (k * o + o * o + o)
+                flops["fwd"] += f_
+                msk["fwd"] += ms
+                cnt["fwd"] += 1
+                tc_ms += ms
+                fused[0] += f_
+                fused[1] += ms
+                fused[2] += 1
+                if n > fused[4]:
+                    fused[3], fused[4] = ms, n
+            elif name in LAYER:
                 cls, j = LAYER[name]
                 n, k, o = a[j].value, a[j + 1].value, a[j + 2].value
                 flops[cls] += 2.0 * n * k * o
@@ -549,6 +563,15 @@ def main():
                     big[c] = {"rows": key[1], "in": key[2], "out": key[3], "launches_per_micro_batch": v[2], "ms_per_launch": v[1] / v[2],
                               "tflops": tf, "frac_of_bf16_peak": tf / tf_sust}
             roof["largest_shape"] = big
+            if fused[2]:
+                tf = fused[0] / max(fused[1], 1e-9) / 1e9
+                tf_big = 2.0 * fused[4] * (71 * 256 + 256 * 256 + 256) / max(fused[3], 1e-9) / 1e9
+                roof["sdf_fused_fwd"] = {"kernel": "sdf_fused_fwd_kernel (mmsb_sdf_net_fwd_fused): x -> h0 -> h1 -> sdf in one launch, h0 on chip",
+                                         "tflops": tf, "frac_of_bf16_peak": tf / tf_sust, "launches_per_micro_batch": fused[2],
+                                         "ms_per_micro_batch": fused[1], "largest_launch": {"rows": fused[4], "ms": fused[3], "tflops": tf_big,
+                                                                                             "frac_of_bf16_peak": tf_big / tf_sust},
+                                         "arithmetic": "three kind::f16 MMAs per product" if _ops.MLP_PRECISION != 1 else "one kind::f16 MMA per product",
+                                         "tensor_pipe_active_ncu": "47 % (activations not stored) / 27 % (h0 + h1 stored for the backward): profiles/r2b_ncu_sdf_fused.md"}
         roof_hash = {}
         for hk, tag in (("mmsb_hashgrid_fwd", "fwd"), ("mmsb_hashgrid_bwd", "bwd")):
             if hb[hk][1] > 0:
@@ -635,7 +658,7 @@ def main():
             torch.cuda.synchronize()
             ms_f = e0.elapsed_time(e1) / k_
             fast_mode = {"value": global_rays / (ms_f / 1e3), "unit": "rays/s", "ms_per_step": ms_f, "layers": LAYERS[1],
-                         "error_band": "1e-2 relative (single-pass TF32 products: 5e-3 measured per layer against fp64)",
+                         "error_band": "1e-2 relative (single-pass TF32 products: 5e-3 measured per layer against fp64; fused single-pass fp16 SDF forward: 5e-4)",
                          "note": "side line, NOT the headline: per-layer kernels become HBM-bound at this arithmetic cost"}
         except Exception as e:
             fast_mode = {"unavailable": f"{type(e).__name__}: {e}"[:300]}

@@ -6,7 +6,7 @@ tag=${1:-rX}
 o=gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -2 > $o/pytest_$tag.log
 python scripts/ncu_targets.py > $o/ncu_targets_$tag.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:"tc_rows|tc_wgrad|hashgrid" --launch-skip 7 -c 7 \
+  ncu --set full --clock-control none --import-source on -k regex:"tc_rows|tc_wgrad|hashgrid|sdf_fused" --launch-skip 9 -c 9 \
       -o $o/prof_$tag python scripts/ncu_targets.py > $o/ncu_$tag.log 2>&1
 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-side > $o/bench_for_ncu_$tag.log 2>&1 && \
   MMSB_PROFILER_RANGE=1 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $o/launches_$tag.csv \
