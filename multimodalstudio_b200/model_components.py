@@ -529,7 +529,7 @@ class RadianceModel(nn.Module):
         if bounds is not None:
             s_ = shape[-1]
             # torch.split: ONE cat in backward (per-modality indexing would zero-fill and add a full-size gradient each)
-            feats = torch.split(radiance_feature, [(b - a) * s_ for a, b in bounds.values()], dim=0)
+            feats = ops.split_rows(radiance_feature, [(b - a) * s_ for a, b in bounds.values()])
             for (mod, (a, b)), feat in zip(bounds.items(), feats):
                 rows = slice(a * s_, b * s_)
                 outputs[mod] = {}

@@ -505,6 +505,66 @@ def packed_weight(w, transpose: bool, precision: int, rows=None):
     return packed
 
 
+class _GradSink:
+    """Shared gradient buffer of the row blocks of one tensor (see split_rows)."""
+    __slots__ = ("buf", "rows", "cols", "claimed")
+
+    def __init__(self, rows, cols):
+        self.buf, self.rows, self.cols, self.claimed = None, rows, cols, set()
+
+    def block(self, off, n, device):
+        """The rows [off, off + n) of the buffer for the FIRST consumer that asks for them (None for any later one: its
+        gradient is then summed by autograd and split_rows falls back to a concatenation)."""
+        if off in self.claimed:
+            return None
+        self.claimed.add(off)
+        if self.buf is None:
+            self.buf = torch.empty((self.rows, self.cols), device=device, dtype=torch.float32)
+        return self.buf[off:off + n]
+
+
+class SplitRowsFn(torch.autograd.Function):
+    """x [N, C] -> consecutive row blocks of the given sizes (torch.split along dim 0).  Backward: when every block's
+    consumer (MLPFn.backward, first layer) has written its input gradient straight into the block's rows of the shared
+    sink buffer, that buffer IS dL/dx — no concatenation pass over N x C; otherwise torch.cat as autograd would do."""
+
+    @staticmethod
+    def forward(ctx, x, sink, *sizes):
+        ctx.sink, ctx.sizes = sink, sizes
+        return tuple(torch.split(x, list(sizes), dim=0))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        sink, sizes = ctx.sink, ctx.sizes
+        buf, sink.buf = sink.buf, None
+        ok, off = buf is not None, 0
+        for g, n in zip(grads, sizes):
+            if n > 0 and ok:
+                ok = (g is not None and g.dim() == 2 and tuple(g.shape) == (n, sink.cols) and g.stride(1) == 1
+                      and g.stride(0) == buf.stride(0) and g.data_ptr() == buf[off].data_ptr())
+            off += n
+        if ok:
+            return (buf, None) + (None,) * len(sizes)
+        dev = next(g.device for g in grads if g is not None)
+        parts = [g if g is not None else torch.zeros((n, sink.cols), device=dev) for g, n in zip(grads, sizes)]
+        return (torch.cat(parts, 0), None) + (None,) * len(sizes)
+
+
+def split_rows(x, sizes):
+    """torch.split(x, sizes, dim=0) for a 2-D x whose blocks feed MLPs (the per-modality heads on the radiance features,
+    model_components.RadianceModel): the blocks carry a handle of a shared gradient buffer, MLPFn writes the input
+    gradient of its first layer into it, and the backward of the split returns the buffer instead of concatenating."""
+    if x.dim() != 2 or not (torch.is_grad_enabled() and x.requires_grad):
+        return torch.split(x, list(sizes), dim=0)
+    sink = _GradSink(x.shape[0], x.shape[1])
+    outs = SplitRowsFn.apply(x, sink, *[int(n) for n in sizes])
+    off = 0
+    for o, n in zip(outs, sizes):
+        o._mmsb_sink = (sink, off)
+        off += int(n)
+    return outs
+
+
 class MLPFn(torch.autograd.Function):
     """y = MLP(x): layers [(W_i [out,in], b_i)], hidden activation, output activation, optional
     skip connections (the layer input becomes cat([h, x]) / sqrt(2), mlp.py:164-165).
@@ -555,6 +615,7 @@ class MLPFn(torch.autograd.Function):
         ctx.save_for_backward(*acts_in, *ws)
         ctx.prec = bwd_prec
         ctx.packed_t = packed_t
+        ctx.sink = getattr(x, "_mmsb_sink", None) if x.dim() == 2 else None
         ctx.cfg = (nl, hidden_act, act_param, out_act, tuple(skips), n_out_used, x.shape, in_dim,
                    [p is not None for p in params], [tuple(params[2 * i].shape) for i in range(nl)])
         return h.reshape(*x.shape[:-1], h.shape[-1])
@@ -613,7 +674,11 @@ class MLPFn(torch.autograd.Function):
                 grads[2 * i + 1] = db
             if i == 0 and not need_dx:
                 break
-            dxin = _padded_rows(n, k, w.device)
+            dxin = None
+            if i == 0 and tc and ctx.sink is not None and 0 not in skips and k == ctx.sink[0].cols and k % 4 == 0:
+                dxin = ctx.sink[0].block(ctx.sink[1], n, w.device)      # straight into the split's shared gradient buffer
+            if dxin is None:
+                dxin = _padded_rows(n, k, w.device)
             # the input of layer i is the hidden activation of layer i-1 (unless a skip concat sits between)
             fuse_prev = i > 0 and i not in skips
             if tc:

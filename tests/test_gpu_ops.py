@@ -646,6 +646,36 @@ def test_sdf_net_fwd_fused_rejects_other_shapes():
         ops.sdf_net_fwd_fused(x, w0, b[:256], w1, b[:256], w2, b, ops.ACT["Softplus"], 100.0, 2)
 
 
+@pytest.mark.parametrize("shared_consumer", [False, True])
+def test_split_rows_gradient_sink(shared_consumer):
+    """ops.split_rows: the blocks' consumers (MLPs) write their input gradients straight into one shared buffer and the
+    split's backward returns it (no concatenation) — same values as torch.split; a block with two consumers (all heads
+    on every modality) falls back to autograd's sum + cat."""
+    from multimodalstudio_b200 import ops
+    torch.manual_seed(3)
+    sizes = [700, 0, 1300, 48]
+    x = torch.randn(sum(sizes), 256, device=DEV, requires_grad=True)
+    ws = [[(torch.randn(64, 256, device=DEV) * 0.1).requires_grad_(), (torch.randn(3, 64, device=DEV) * 0.1).requires_grad_()] for _ in sizes]
+    bs = [[torch.zeros(64, device=DEV, requires_grad=True), torch.zeros(3, device=DEV, requires_grad=True)] for _ in sizes]
+
+    def run(split):
+        loss = 0.0
+        for i, blk in enumerate(split(x * 1.0, sizes)):
+            if blk.shape[0] == 0:
+                continue
+            loss = loss + ops.mlp_forward(blk, ws[i], bs[i], "ReLU", "Sigmoid").square().sum()
+            if shared_consumer and i == 0:
+                loss = loss + ops.mlp_forward(blk, ws[2], bs[2], "ReLU", "Sigmoid").sum()
+        return torch.autograd.grad(loss, [x] + [w for pair in ws for w in pair], allow_unused=True)
+
+    got = run(ops.split_rows)
+    ref = run(lambda t, sz: torch.split(t, sz, dim=0))
+    for a, r in zip(got, ref):
+        assert (a is None) == (r is None)
+        if a is not None:
+            assert_close(a, r, rtol=1e-6, atol=1e-9, what="split_rows gradient")
+
+
 def test_decimated_losses_golden():
     """Preset grid_decimated: LossManager's per_channel_probability losses against the reference fixture (the channel
     draws of the reference are injected), value and gradient; and the preset builds + draws on its own."""
