@@ -529,7 +529,8 @@ class RadianceModel(nn.Module):
         if bounds is not None:
             s_ = shape[-1]
             # torch.split: ONE cat in backward (per-modality indexing would zero-fill and add a full-size gradient each)
-            feats = ops.split_rows(radiance_feature, [(b - a) * s_ for a, b in bounds.values()])
+            one_head = heads is not None and all(len(heads[m]) == 1 for m in bounds)
+            feats = ops.split_rows(radiance_feature, [(b - a) * s_ for a, b in bounds.values()], single_consumer=one_head)
             for (mod, (a, b)), feat in zip(bounds.items(), feats):
                 rows = slice(a * s_, b * s_)
                 outputs[mod] = {}

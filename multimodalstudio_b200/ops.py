@@ -505,12 +505,21 @@ def packed_weight(w, transpose: bool, precision: int, rows=None):
     return packed
 
 
+class _OutActToken:
+    """Shared between the MLP that produced a tensor y = act(z) and the split_rows that consumes it: when `applied` is
+    set, the gradient the producer receives is already dL/dz (the consumers folded act'(y) into their dgrad epilogues)."""
+    __slots__ = ("act", "act_param", "applied")
+
+    def __init__(self, act, act_param):
+        self.act, self.act_param, self.applied = act, act_param, False
+
+
 class _GradSink:
     """Shared gradient buffer of the row blocks of one tensor (see split_rows)."""
-    __slots__ = ("buf", "rows", "cols", "claimed")
+    __slots__ = ("buf", "rows", "cols", "claimed", "token")
 
-    def __init__(self, rows, cols):
-        self.buf, self.rows, self.cols, self.claimed = None, rows, cols, set()
+    def __init__(self, rows, cols, token=None):
+        self.buf, self.rows, self.cols, self.claimed, self.token = None, rows, cols, set(), token
 
     def block(self, off, n, device):
         """The rows [off, off + n) of the buffer for the FIRST consumer that asks for them (None for any later one: its
@@ -531,32 +540,56 @@ class SplitRowsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, sink, *sizes):
         ctx.sink, ctx.sizes = sink, sizes
+        if sink.token is not None:
+            ctx.save_for_backward(x)
         return tuple(torch.split(x, list(sizes), dim=0))
 
     @staticmethod
     def backward(ctx, *grads):
         sink, sizes = ctx.sink, ctx.sizes
         buf, sink.buf = sink.buf, None
-        ok, off = buf is not None, 0
+        tok = sink.token
+        in_sink, off = [], 0
         for g, n in zip(grads, sizes):
-            if n > 0 and ok:
-                ok = (g is not None and g.dim() == 2 and tuple(g.shape) == (n, sink.cols) and g.stride(1) == 1
-                      and g.stride(0) == buf.stride(0) and g.data_ptr() == buf[off].data_ptr())
+            in_sink.append(n == 0 or (buf is not None and g is not None and g.dim() == 2 and tuple(g.shape) == (n, sink.cols)
+                                      and g.stride(1) == 1 and g.stride(0) == buf.stride(0) and g.data_ptr() == buf[off].data_ptr()))
             off += n
-        if ok:
+        if all(in_sink):
+            if tok is not None:
+                tok.applied = True
             return (buf, None) + (None,) * len(sizes)
         dev = next(g.device for g in grads if g is not None)
         parts = [g if g is not None else torch.zeros((n, sink.cols), device=dev) for g, n in zip(grads, sizes)]
+        if tok is not None:
+            # the blocks that went through the sink already carry act'(y); bring the others to the same state
+            (y,) = ctx.saved_tensors
+            off = 0
+            for i, n in enumerate(sizes):
+                if n > 0 and not in_sink[i] and grads[i] is not None:
+                    gi, yi = _rows(parts[i], sink.cols), y[off:off + n]
+                    out = torch.empty((n, sink.cols), device=dev, dtype=torch.float32)
+                    call("mmsb_act_bwd", ptr(gi), _i64(gi.stride(0)), ptr(yi), _i64(yi.stride(0)), ptr(out), _i64(out.stride(0)),
+                         _i64(n), _i32(sink.cols), _i32(tok.act), _f32(tok.act_param), stream_ptr())
+                    parts[i] = out
+                off += n
+            tok.applied = True
         return (torch.cat(parts, 0), None) + (None,) * len(sizes)
 
 
-def split_rows(x, sizes):
+SPLIT_FOLD = int(os.environ.get("MMSB_SPLIT_FOLD", "1"))     # dev switch: 0 keeps the producer's own activation-derivative pass
+
+
+def split_rows(x, sizes, single_consumer: bool = False):
     """torch.split(x, sizes, dim=0) for a 2-D x whose blocks feed MLPs (the per-modality heads on the radiance features,
     model_components.RadianceModel): the blocks carry a handle of a shared gradient buffer, MLPFn writes the input
-    gradient of its first layer into it, and the backward of the split returns the buffer instead of concatenating."""
+    gradient of its first layer into it, and the backward of the split returns the buffer instead of concatenating.
+    `single_consumer` (every block feeds exactly ONE MLP): when x is the output y = act(z) of an MLP, that MLP's
+    output-activation derivative is folded into the consumers' dgrad epilogues (dx = (dz W) * act'(y): the epilogue's
+    `y_prev` operand) instead of a pass of its own over x."""
     if x.dim() != 2 or not (torch.is_grad_enabled() and x.requires_grad):
         return torch.split(x, list(sizes), dim=0)
-    sink = _GradSink(x.shape[0], x.shape[1])
+    token = getattr(x, "_mmsb_out_act", None) if (single_consumer and SPLIT_FOLD) else None
+    sink = _GradSink(x.shape[0], x.shape[1], token)
     outs = SplitRowsFn.apply(x, sink, *[int(n) for n in sizes])
     off = 0
     for o, n in zip(outs, sizes):
@@ -573,7 +606,7 @@ class MLPFn(torch.autograd.Function):
     (the sdf-only evaluations of surface_model.py:143-146 / get_sdf)."""
 
     @staticmethod
-    def forward(ctx, x, hidden_act, act_param, out_act, skips, n_out_used, *params):
+    def forward(ctx, x, hidden_act, act_param, out_act, skips, n_out_used, out_token, *params):
         nl = len(params) // 2
         in_dim = x.shape[-1]
         x2 = _rows(x, in_dim)
@@ -616,6 +649,7 @@ class MLPFn(torch.autograd.Function):
         ctx.prec = bwd_prec
         ctx.packed_t = packed_t
         ctx.sink = getattr(x, "_mmsb_sink", None) if x.dim() == 2 else None
+        ctx.out_token = out_token
         ctx.cfg = (nl, hidden_act, act_param, out_act, tuple(skips), n_out_used, x.shape, in_dim,
                    [p is not None for p in params], [tuple(params[2 * i].shape) for i in range(nl)])
         return h.reshape(*x.shape[:-1], h.shape[-1])
@@ -631,8 +665,8 @@ class MLPFn(torch.autograd.Function):
         n = acts[0].shape[0]
         out_dim = acts[nl].shape[1]
         dz = _rows(dy.reshape(n, out_dim) if dy.dim() != 2 else dy, out_dim)
-        # activation derivative of the output layer
-        if out_act != 0:
+        # activation derivative of the output layer (unless the consumers of the output have folded it into their dgrads)
+        if out_act != 0 and not (ctx.out_token is not None and ctx.out_token.applied):
             dz_new = _padded_rows(n, out_dim, dz.device)
             call("mmsb_act_bwd", ptr(dz), _i64(dz.stride(0)), ptr(acts[nl]), _i64(acts[nl].stride(0)), ptr(dz_new),
                  _i64(dz_new.stride(0)), _i64(n), _i32(out_dim), _i32(out_act), _f32(act_param), stream_ptr())
@@ -640,7 +674,7 @@ class MLPFn(torch.autograd.Function):
         grads = [None] * (2 * nl)
         dx_skip = None
         need_dx = ctx.needs_input_grad[0]
-        want = [ctx.needs_input_grad[6 + 2 * i] or (has[2 * i + 1] and ctx.needs_input_grad[7 + 2 * i]) for i in range(nl)]
+        want = [ctx.needs_input_grad[7 + 2 * i] or (has[2 * i + 1] and ctx.needs_input_grad[8 + 2 * i]) for i in range(nl)]
         shapes = []
         for i in range(nl):
             if want[i]:
@@ -674,14 +708,18 @@ class MLPFn(torch.autograd.Function):
                 grads[2 * i + 1] = db
             if i == 0 and not need_dx:
                 break
-            dxin = None
+            dxin, fold = None, None
             if i == 0 and tc and ctx.sink is not None and 0 not in skips and k == ctx.sink[0].cols and k % 4 == 0:
                 dxin = ctx.sink[0].block(ctx.sink[1], n, w.device)      # straight into the split's shared gradient buffer
+                if dxin is not None:
+                    fold = ctx.sink[0].token     # x = act(z) of the producing MLP: fold act'(x) into this dgrad's epilogue
             if dxin is None:
                 dxin = _padded_rows(n, k, w.device)
             # the input of layer i is the hidden activation of layer i-1 (unless a skip concat sits between)
             fuse_prev = i > 0 and i not in skips
-            if tc:
+            if tc and fold is not None:
+                linear_bwd_data_tc(dz, ctx.packed_t[i], k, xin, fold.act, fold.act_param, prec, out=dxin)
+            elif tc:
                 linear_bwd_data_tc(dz, ctx.packed_t[i], k, xin if fuse_prev else None,
                                    hidden_act if fuse_prev else 0, act_param, prec, out=dxin)
             else:
@@ -707,7 +745,7 @@ class MLPFn(torch.autograd.Function):
         if need_dx:
             dx = dz if dx_skip is None else dz + dx_skip
             dx = dx.reshape(x_shape)
-        return (dx, None, None, None, None, None, *grads)
+        return (dx, None, None, None, None, None, None, *grads)
 
 
 class SdfNetFn(torch.autograd.Function):
@@ -867,7 +905,13 @@ def mlp_forward(x, weights: Sequence[torch.Tensor], biases: Sequence[Optional[to
     params = []
     for w, b in zip(weights, biases):
         params += [w, b]
-    return MLPFn.apply(x, ACT[hidden_act], float(act_param), ACT[out_act], tuple(skips), n_out_used, *params)
+    # an output activation whose derivative depends on the output only (ReLU) can be folded into the consumers' dgrads:
+    # the token travels on the output tensor to ops.split_rows
+    token = _OutActToken(ACT[out_act], float(act_param)) if out_act == "ReLU" else None
+    out = MLPFn.apply(x, ACT[hidden_act], float(act_param), ACT[out_act], tuple(skips), n_out_used, token, *params)
+    if token is not None and out.dim() == 2:
+        out._mmsb_out_act = token
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -649,31 +649,43 @@ def test_sdf_net_fwd_fused_rejects_other_shapes():
 @pytest.mark.parametrize("shared_consumer", [False, True])
 def test_split_rows_gradient_sink(shared_consumer):
     """ops.split_rows: the blocks' consumers (MLPs) write their input gradients straight into one shared buffer and the
-    split's backward returns it (no concatenation) — same values as torch.split; a block with two consumers (all heads
+    split's backward returns it (no concatenation) — same values as torch.split; with one consumer per block the
+    producing MLP's ReLU derivative is folded into the consumers' dgrad epilogues; a block with two consumers (all heads
     on every modality) falls back to autograd's sum + cat."""
     from multimodalstudio_b200 import ops
     torch.manual_seed(3)
     sizes = [700, 0, 1300, 48]
-    x = torch.randn(sum(sizes), 256, device=DEV, requires_grad=True)
+    x0 = torch.randn(sum(sizes), 128, device=DEV, requires_grad=True)
+    wp = [(torch.randn(256, 128, device=DEV) * 0.1).requires_grad_(), (torch.randn(256, 256, device=DEV) * 0.1).requires_grad_()]
+    bp = [torch.zeros(256, device=DEV, requires_grad=True), (torch.randn(256, device=DEV) * 0.1).requires_grad_()]
     ws = [[(torch.randn(64, 256, device=DEV) * 0.1).requires_grad_(), (torch.randn(3, 64, device=DEV) * 0.1).requires_grad_()] for _ in sizes]
     bs = [[torch.zeros(64, device=DEV, requires_grad=True), torch.zeros(3, device=DEV, requires_grad=True)] for _ in sizes]
 
     def run(split):
+        x = ops.mlp_forward(x0, wp, bp, "ReLU", "ReLU")            # the producer: y = relu(W1 relu(W0 x0 + b0) + b1)
         loss = 0.0
-        for i, blk in enumerate(split(x * 1.0, sizes)):
+        for i, blk in enumerate(split(x, sizes)):
             if blk.shape[0] == 0:
                 continue
             loss = loss + ops.mlp_forward(blk, ws[i], bs[i], "ReLU", "Sigmoid").square().sum()
             if shared_consumer and i == 0:
                 loss = loss + ops.mlp_forward(blk, ws[2], bs[2], "ReLU", "Sigmoid").sum()
-        return torch.autograd.grad(loss, [x] + [w for pair in ws for w in pair], allow_unused=True)
+        return torch.autograd.grad(loss, [x0] + wp + bp + [w for pair in ws for w in pair], allow_unused=True)
 
-    got = run(ops.split_rows)
+    got = run(lambda t, sz: ops.split_rows(t, sz, single_consumer=not shared_consumer))
     ref = run(lambda t, sz: torch.split(t, sz, dim=0))
     for a, r in zip(got, ref):
         assert (a is None) == (r is None)
         if a is not None:
             assert_close(a, r, rtol=1e-6, atol=1e-9, what="split_rows gradient")
+    # a consumer that does not go through the sink (plain torch op on one block): the fold still yields the same gradients
+    def run_mixed(split):
+        x = ops.mlp_forward(x0, wp, bp, "ReLU", "ReLU")
+        blks = split(x, sizes)
+        loss = ops.mlp_forward(blks[0], ws[0], bs[0], "ReLU", "Sigmoid").square().sum() + (blks[2] * blks[2]).sum()
+        return torch.autograd.grad(loss, [x0] + wp, allow_unused=True)
+    for a, r in zip(run_mixed(lambda t, sz: ops.split_rows(t, sz, single_consumer=True)), run_mixed(lambda t, sz: torch.split(t, sz, dim=0))):
+        assert_close(a, r, rtol=1e-6, atol=1e-9, what="split_rows gradient (mixed consumers)")
 
 
 def test_decimated_losses_golden():
