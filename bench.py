@@ -571,7 +571,7 @@ def main():
                                          "ms_per_micro_batch": fused[1], "largest_launch": {"rows": fused[4], "ms": fused[3], "tflops": tf_big,
                                                                                              "frac_of_bf16_peak": tf_big / tf_sust},
                                          "arithmetic": "three kind::f16 MMAs per product" if _ops.MLP_PRECISION != 1 else "one kind::f16 MMA per product",
-                                         "tensor_pipe_active_ncu": "47 % (activations not stored) / 27 % (h0 + h1 stored for the backward): profiles/r2b_ncu_full.md"}
+                                         "tensor_pipe_active_ncu": "47 % (activations not stored) / 27 % (h0 + h1 stored for the backward): profiles/r2b_ncu_full.md, profiles/r2c_ncu_full.md"}
         roof_hash = {}
         for hk, tag in (("mmsb_hashgrid_fwd", "fwd"), ("mmsb_hashgrid_bwd", "bwd")):
             if hb[hk][1] > 0:

@@ -16,7 +16,9 @@
 //                          layer-1 MMAs of a chunk run while the next chunk is produced; layer 1: bias / activation /
 //                          dot product with the head's weights -> one float per row.
 // h0 / h1 are written to global memory only when the caller needs them (training: the backward kernels read them; a
-// `group` > 1 keeps only every group-th row of h1 = the centre rows whose geometry features the caller evaluates).
+// `group` > 1 keeps only every group-th row of h1 = the centre rows whose geometry features the caller evaluates), as
+// 32-row blocks through cp.async.bulk.tensor stores (layer 1's blocks are staged in the h0 operand ring, idle by then).
+// Waiting roles poll their mbarriers with a nanosleep back-off: the epilogue warps are issue-bound.
 #include "tc_common.cuh"
 
 namespace mmsb {
