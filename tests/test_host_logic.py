@@ -72,3 +72,24 @@ def test_update_config_and_errors():
     assert [tuple(l.weight.shape) for l in mlp.surface_model.surface_field.field.layers][4] == (256, 295)   # skip at layer 4
     bg = build_model("grid_raw_grid_bg_unbalanced", modalities={"rgb": 3, "polarization": 4}, log2_hashmap_size=8)
     assert bg.background_model.background_field.base_field.feature_grid.radius == 2
+
+
+def test_split_rows_falls_back_to_autograd_semantics_on_cpu():
+    """ops.split_rows without sink-writing consumers (plain torch ops on CPU tensors): the backward is autograd's zero-fill +
+    concatenation, block by block — same gradient as torch.split, also for an unused and an empty block."""
+    import torch
+    from multimodalstudio_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(10, 4, requires_grad=True)
+    sizes = [3, 0, 5, 2]
+
+    def loss_of(blocks):
+        return (blocks[0] ** 2).sum() + (blocks[2] * 3.0).sum()          # block 3 unused, block 1 empty
+
+    g1, = torch.autograd.grad(loss_of(ops.split_rows(x * 1.0, sizes)), x)
+    g2, = torch.autograd.grad(loss_of(torch.split(x * 1.0, sizes, dim=0)), x)
+    assert torch.equal(g1, g2)
+    # no autograd: plain views
+    with torch.no_grad():
+        blocks = ops.split_rows(x, sizes)
+    assert [b.shape[0] for b in blocks] == sizes and not hasattr(blocks[0], "_mmsb_sink")
