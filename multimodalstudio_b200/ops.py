@@ -585,7 +585,8 @@ def split_rows(x, sizes, single_consumer: bool = False):
     gradient of its first layer into it, and the backward of the split returns the buffer instead of concatenating.
     `single_consumer` (every block feeds exactly ONE MLP): when x is the output y = act(z) of an MLP, that MLP's
     output-activation derivative is folded into the consumers' dgrad epilogues (dx = (dz W) * act'(y): the epilogue's
-    `y_prev` operand) instead of a pass of its own over x."""
+    `y_prev` operand) instead of a pass of its own over x.  The caller guarantees that x has no consumer besides this
+    split (RadianceModel: the radiance features only feed the heads); without that guarantee pass False."""
     if x.dim() != 2 or not (torch.is_grad_enabled() and x.requires_grad):
         return torch.split(x, list(sizes), dim=0)
     token = getattr(x, "_mmsb_out_act", None) if (single_consumer and SPLIT_FOLD) else None
