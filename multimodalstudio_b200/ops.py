@@ -246,6 +246,40 @@ def _piece_width(p):
     return p[4].num_levels * p[4].features_per_level
 
 
+# Zero-copy "copy" pieces.  A wide materialised piece (the SDF network's 256 geometry features in the radiance MLP's input
+# row, radiance_field.py:90-101) costs a pass over 2 x n x 256 floats when it is copied into the assembled row.  Instead
+# the producer writes it where it will be needed: AssembleFn records where a wide copy piece ended up (_ROW_HINT: rows,
+# width -> leading dimension, total width, column); on the next call the producer (`row_slot`) allocates the whole row
+# buffer, registers it (_ROW_BUFS) and returns the piece's column slice as its output; AssembleFn recognises the slice by
+# its storage and ADOPTS the buffer as its output — the other pieces are written around the one that is already there.
+# Any mismatch (another preset, a reshaped piece, a stale hint) falls back to the copy.
+_ROW_HINT = {}
+_ROW_BUFS = {}
+ROW_ADOPT = int(os.environ.get("MMSB_ROW_ADOPT", "1"))
+ROW_ADOPT_MIN_WIDTH = 64
+ROW_ADOPTIONS = 0            # how often AssembleFn adopted a producer's row buffer (tests / dev)
+
+
+def row_slot(n: int, width: int, device):
+    """Output buffer [n, width] for a producer whose result will be a copy piece of an assembled row: a column slice of a
+    fresh, registered row buffer when the layout is known from an earlier call, else a plain tensor."""
+    hint = _ROW_HINT.get((n, width)) if ROW_ADOPT else None
+    if hint is None:
+        return torch.empty((n, width), device=device, dtype=torch.float32)
+    ld, total, col = hint
+    buf = torch.empty((n, ld), device=device, dtype=torch.float32)
+    _ROW_BUFS[buf.untyped_storage().data_ptr()] = (n, ld, total, col, width)
+    return buf[:, col:col + width]
+
+
+def _adoptable(t, n, ld, total, col, width):
+    if not (ROW_ADOPT and t.dim() == 2 and t.is_cuda and t.dtype == torch.float32 and t.stride(1) == 1 and t.stride(0) == ld):
+        return False
+    st = t.untyped_storage()
+    return (_ROW_BUFS.get(st.data_ptr()) == (n, ld, total, col, width) and t.storage_offset() == col
+            and st.nbytes() >= n * ld * 4)
+
+
 class AssembleFn(torch.autograd.Function):
     """rows = cat(pieces, -1), every piece written by its producer kernel straight into its column range of one
     16-byte-aligned row buffer (no torch.cat, no second pass); backward reads the column ranges of the incoming
@@ -265,13 +299,31 @@ class AssembleFn(torch.autograd.Function):
                 widths.append(p[4].num_levels * p[4].features_per_level)
         total = sum(widths)
         dev = tensors[0].device
-        out = _padded_rows(n, total, dev)
+        ld = (total + 3) // 4 * 4
+        out, in_place, col = None, None, 0
+        for i, (p, w) in enumerate(zip(spec, widths)):
+            if p[0] == "copy" and w >= ROW_ADOPT_MIN_WIDTH:
+                t = tensors[p[1]]
+                if out is None and _adoptable(t, n, ld, total, col, w):
+                    # the piece already sits in its column range of a row buffer of this very layout: adopt the buffer
+                    _ROW_BUFS.pop(t.untyped_storage().data_ptr(), None)
+                    global ROW_ADOPTIONS
+                    ROW_ADOPTIONS += 1
+                    # (a fresh tensor over the same storage, not an autograd view of the piece)
+                    out = torch.empty((0,), device=dev, dtype=torch.float32).set_(t.untyped_storage(), 0, (n, total), (ld, 1))
+                    in_place = i
+                elif t.dim() == 2 and t.shape[0] == n:
+                    _ROW_HINT[(n, w)] = (ld, total, col)
+            col += w
+        if out is None:
+            out = _padded_rows(n, total, dev)
         saved, col = {}, 0
-        for p, w in zip(spec, widths):
+        for i, (p, w) in enumerate(zip(spec, widths)):
             if p[0] == "copy":
-                src = _rows(tensors[p[1]].reshape(n, w), w)
-                call("mmsb_copy_rows", ptr(src), _i64(src.stride(0)), ptr(out[:, col:]), _i64(out.stride(0)), _i64(n),
-                     _i32(w), stream_ptr())
+                if i != in_place:
+                    src = _rows(tensors[p[1]].reshape(n, w), w)
+                    call("mmsb_copy_rows", ptr(src), _i64(src.stride(0)), ptr(out[:, col:]), _i64(out.stride(0)), _i64(n),
+                         _i32(w), stream_ptr())
             elif p[0] == "nerf":
                 x2 = saved.setdefault(p[1], _rows(tensors[p[1]], tensors[p[1]].shape[-1]))
                 nerf_fwd_into(x2, list(p[2]), p[3], out, col)
@@ -460,6 +512,7 @@ def clear_pack_cache() -> None:
     """Call after every optimiser step (the packed operands are functions of the weights)."""
     _PACK_CACHE.clear()
     _PERM_CACHE.clear()
+    _ROW_BUFS.clear()
 
 
 _PERM_CACHE = {}
@@ -801,7 +854,8 @@ class SdfNetFn(torch.autograd.Function):
             if n_full > 0:
                 h1c = h1 if h1_group > 1 else (h1[0::group] if group > 1 else h1[:n_full])
                 p2 = 1 if prec == 1 else 3
-                geo = linear_fwd_tc(h1c, packed_weight(w2, False, p2, rows=(1, g_dim + 1)), bs[2][1:], g_dim, 0, 1.0, p2)
+                geo = linear_fwd_tc(h1c, packed_weight(w2, False, p2, rows=(1, g_dim + 1)), bs[2][1:], g_dim, 0, 1.0, p2,
+                                    out=row_slot(n_full, g_dim, dev))
         else:
             amaxes = torch.zeros((2,), device=dev, dtype=torch.float32) if mode2 else None
             p0 = layer_precision(x2, ws[0].shape[0]) if mode2 else prec
@@ -820,7 +874,7 @@ class SdfNetFn(torch.autograd.Function):
                 h1c = h1[0::group] if group > 1 else h1[:n_full]
                 p2 = layer_precision(h1c, g_dim) if mode2 else prec
                 geo = linear_fwd_tc(h1c, packed_weight(w2, False, p2, rows=(1, g_dim + 1)), bs[2][1:], g_dim, 0, 1.0, p2,
-                                    x_amax=amaxes[1:2] if p2 == 2 else None)
+                                    out=row_slot(n_full, g_dim, dev), x_amax=amaxes[1:2] if p2 == 2 else None)
         if mode2:
             prec = 3
         ctx.cfg = (n, n_full, group, act, act_param, prec, in_dim, x.shape)

@@ -688,6 +688,51 @@ def test_split_rows_gradient_sink(shared_consumer):
         assert_close(a, r, rtol=1e-6, atol=1e-9, what="split_rows gradient (mixed consumers)")
 
 
+def test_assemble_adopts_a_piece_that_is_already_in_place():
+    """ops.row_slot / AssembleFn: once the layout of an assembled row is known, the producer of a wide copy piece writes
+    into its column range of the row buffer and assemble adopts that buffer (no copy) — identical rows and gradients to
+    the copying path; a piece of another shape, or a stale hint, falls back to the copy."""
+    from multimodalstudio_b200 import ops
+    torch.manual_seed(5)
+    n = 3000
+    ops._ROW_HINT.clear(); ops._ROW_BUFS.clear()
+    pos = torch.rand(n, 3, device=DEV) * 2 - 1
+    freqs = [1.0, 2.0, 4.0, 8.0]
+    src = torch.randn(n, 256, device=DEV)
+    nv = torch.randn(n, 1, device=DEV)
+
+    def build(geo):
+        return ops.assemble([ops.copy_piece(pos), ops.nerf_piece(pos, freqs, True), ops.copy_piece(geo), ops.copy_piece(nv)])
+
+    geo1 = ops.row_slot(n, 256, DEV)                   # no hint yet: a plain tensor
+    assert geo1.is_contiguous()
+    geo1.copy_(src)
+    rows1 = build(geo1.requires_grad_())
+    assert (n, 256) in ops._ROW_HINT
+    geo2 = ops.row_slot(n, 256, DEV)                   # now a column slice of a registered row buffer
+    assert not geo2.is_contiguous() and geo2.stride(0) == rows1.stride(0)
+    geo2.copy_(src)
+    launches = ops._lib.launch_count() if hasattr(ops, "_lib") else None
+    geo2.requires_grad_()
+    rows2 = build(geo2)
+    assert rows2.untyped_storage().data_ptr() == geo2.untyped_storage().data_ptr(), "the row buffer was not adopted"
+    assert torch.equal(rows1, rows2)
+    w = torch.randn_like(rows1)
+    g1, = torch.autograd.grad((rows1 * w).sum(), geo1)
+    g2, = torch.autograd.grad((rows2 * w).sum(), geo2)
+    assert torch.equal(g1, g2)
+    # another number of rows: the hint does not apply, a stale registration is never adopted
+    other = ops.row_slot(n + 1, 256, DEV)
+    assert other.is_contiguous()
+    geo3 = ops.row_slot(n, 256, DEV)
+    geo3.copy_(src)
+    rows3 = ops.assemble([ops.copy_piece(pos), ops.copy_piece(geo3)])        # a different layout: must copy
+    assert rows3.untyped_storage().data_ptr() != geo3.untyped_storage().data_ptr()
+    assert torch.equal(rows3[:, 3:], src)
+    ops.clear_pack_cache()
+    assert not ops._ROW_BUFS
+
+
 def test_decimated_losses_golden():
     """Preset grid_decimated: LossManager's per_channel_probability losses against the reference fixture (the channel
     draws of the reference are injected), value and gradient; and the preset builds + draws on its own."""
